@@ -1,0 +1,175 @@
+// Observation-major evaluation kernels: PySBA.rotate / project / fun (pySBA.py:61-101),
+// the analytic Jacobian blocks that replace scipy's 3-point finite difference
+// (scipy/optimize/_numdiff.py:770) and the sparsity pattern (pySBA.py:103-118).
+#pragma once
+#include "common.cuh"
+
+namespace lcba {
+
+// ---- camera tables -----------------------------------------------------------------
+__global__ void k_cam_tables(const double* __restrict__ cams, double* __restrict__ tab, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) cam_table_build(cams + (size_t)c * NCP, tab + (size_t)c * CAMTAB);
+}
+
+__device__ __forceinline__ void load_tables_smem(const double* __restrict__ tab, double* s_tab,
+                                                 int C) {
+  for (int i = threadIdx.x; i < C * CAMTAB; i += blockDim.x) s_tab[i] = tab[i];
+}
+
+// ---- row-wise API kernels (arbitrary gathered rows; not the solver's hot loop) -----
+__global__ void k_rotate_rows(const double* __restrict__ pts, const double* __restrict__ rv,
+                              double* __restrict__ out, long long M) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  double ox, oy, oz;
+  rotate_row(rv[3 * i], rv[3 * i + 1], rv[3 * i + 2], pts[3 * i], pts[3 * i + 1], pts[3 * i + 2],
+             ox, oy, oz);
+  out[3 * i] = ox;
+  out[3 * i + 1] = oy;
+  out[3 * i + 2] = oz;
+}
+
+__global__ void k_project_rows(const double* __restrict__ pts, const double* __restrict__ cams,
+                               double* __restrict__ out, long long M) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  const double* cm = cams + i * NCP;
+  double x, y, z;
+  rotate_row(cm[0], cm[1], cm[2], pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], x, y, z);
+  x += cm[3];
+  y += cm[4];
+  z += cm[5];
+  x /= z;
+  y /= z;
+  const double n = x * x + y * y;
+  const double r = 1.0 + cm[7] * n + cm[8] * n * n;   // pySBA.py:86
+  const double rf = r * cm[6];
+  out[2 * i] = x * rf + cm[9];
+  out[2 * i + 1] = y * rf + cm[10];
+}
+
+// ---- fun: residual (+ cost) over the resident, point-major observation stream ------
+// r_out may be null. perm (original index of sorted observation i) may be null (identity).
+// Block partial of sum(r^2) goes to part[blockIdx.x].
+__global__ void __launch_bounds__(256)
+k_residual(const double* __restrict__ tab, const double* __restrict__ pts,
+           const double2* __restrict__ uv, const uint8_t* __restrict__ cam,
+           const int32_t* __restrict__ pt, const double* __restrict__ wgt,
+           const int32_t* __restrict__ perm, long long N, int C, double2* __restrict__ r_out,
+           double* __restrict__ part) {
+  extern __shared__ double s_dyn[];
+  double* s_tab = s_dyn;
+  __shared__ double s_red[32];
+  load_tables_smem(tab, s_tab, C);
+  __syncthreads();
+  double acc = 0.0;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+    const int c = cam[i];
+    const long long p = pt[i];
+    const double2 o = uv[i];
+    const double w = wgt ? wgt[i] : 1.0;
+    double pu, pv;
+    project_tab(s_tab + c * CAMTAB, pts[3 * p], pts[3 * p + 1], pts[3 * p + 2], pu, pv);
+    const double ru = w * (pu - o.x), rv = w * (pv - o.y);
+    acc = fma(ru, ru, fma(rv, rv, acc));
+    if (r_out) {
+      const long long dst = perm ? (long long)perm[i] : i;
+      r_out[dst] = make_double2(ru, rv);
+    }
+  }
+  const double s = block_sum(acc, s_red);
+  if (threadIdx.x == 0) part[blockIdx.x] = s;
+}
+
+// ---- residual + Jacobian blocks materialised to HBM (metric M1) --------------------
+// One thread per observation; each warp stages its 32 x (2x11 | 2x3) blocks in shared
+// memory and streams them out with coalesced 128-bit stores.  264 B/obs algorithmic.
+constexpr int JB_THREADS = 256;
+constexpr int JB_STAGE = 22 + 6;   // doubles per observation in the staging tile
+constexpr int JB_LD = 33;           // odd leading dimension: conflict-free transpose
+
+__global__ void __launch_bounds__(JB_THREADS)
+k_jacobian_blocks(const double* __restrict__ tab, const double* __restrict__ pts,
+                  const double2* __restrict__ uv, const uint8_t* __restrict__ cam,
+                  const int32_t* __restrict__ pt, const double* __restrict__ wgt,
+                  const int32_t* __restrict__ perm, long long N, int C,
+                  double2* __restrict__ r_out, double* __restrict__ Jc_out,
+                  double* __restrict__ Jp_out) {
+  extern __shared__ double s_dyn[];
+  double* s_tab = s_dyn;                                         // C*CAMTAB
+  double* s_stage = s_dyn + ((C * CAMTAB + 1) & ~1);             // warps * JB_LD * JB_STAGE
+  load_tables_smem(tab, s_tab, C);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  double* st = s_stage + (size_t)wid * JB_LD * JB_STAGE;
+  const long long nwarps_total = (long long)gridDim.x * (JB_THREADS / 32);
+  const long long ngroups = (N + 31) / 32;
+  for (long long g = (long long)blockIdx.x * (JB_THREADS / 32) + wid; g < ngroups;
+       g += nwarps_total) {
+    const long long i = g * 32 + lane;
+    const bool active = i < N;
+    double w = 1.0;
+    if (active) {
+      const int c = cam[i];
+      const long long p = pt[i];
+      const double2 o = uv[i];
+      w = wgt ? wgt[i] : 1.0;
+      ObsLin L;
+      obs_linearize<true>(s_tab + c * CAMTAB, pts[3 * p], pts[3 * p + 1], pts[3 * p + 2], o.x, o.y,
+                          w, L);
+      if (r_out) r_out[perm ? (long long)perm[i] : i] = make_double2(L.ru, L.rv);
+      // element-major staging: element a of this lane at st[a*JB_LD + lane]
+#pragma unroll
+      for (int a = 0; a < 9; ++a) {
+        st[a * JB_LD + lane] = L.Jc[0][a];
+        st[(11 + a) * JB_LD + lane] = L.Jc[1][a];
+      }
+      st[9 * JB_LD + lane] = w;
+      st[10 * JB_LD + lane] = 0.0;
+      st[20 * JB_LD + lane] = 0.0;
+      st[21 * JB_LD + lane] = w;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        st[(22 + a) * JB_LD + lane] = L.Jp[0][a];
+        st[(25 + a) * JB_LD + lane] = L.Jp[1][a];
+      }
+    }
+    __syncwarp();
+    const long long base = g * 32;
+    const int nvalid = (int)min((long long)32, N - base);
+    if (!perm) {
+      // contiguous output: Jc rows [base, base+nvalid) x 22, Jp x 6
+      double* jc = Jc_out + base * 22;
+      for (int e = lane; e < nvalid * 22; e += 32) jc[e] = st[(e % 22) * JB_LD + (e / 22)];
+      double* jp = Jp_out + base * 6;
+      for (int e = lane; e < nvalid * 6; e += 32) jp[e] = st[(22 + e % 6) * JB_LD + (e / 6)];
+    } else {
+      for (int e = lane; e < nvalid * 22; e += 32) {
+        const int ob = e / 22;
+        Jc_out[(long long)perm[base + ob] * 22 + (e % 22)] = st[(e % 22) * JB_LD + ob];
+      }
+      for (int e = lane; e < nvalid * 6; e += 32) {
+        const int ob = e / 6;
+        Jp_out[(long long)perm[base + ob] * 6 + (e % 6)] = st[(22 + e % 6) * JB_LD + ob];
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ---- bundle_adjustment_sparsity (pySBA.py:103-118) ---------------------------------
+// 14 sorted column indices per row, rows 2i and 2i+1 identical.  One thread per entry.
+__global__ void k_sparsity_indices(const long long* __restrict__ cam_idx,
+                                   const long long* __restrict__ pt_idx, long long N, int C,
+                                   int32_t* __restrict__ out) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= N * 28) return;
+  const long long i = e / 28;
+  const int j = (int)(e % 14);
+  out[e] = (j < NCP) ? (int32_t)(cam_idx[i] * NCP + j)
+                     : (int32_t)((long long)C * NCP + pt_idx[i] * 3 + (j - NCP));
+}
+
+}  // namespace lcba

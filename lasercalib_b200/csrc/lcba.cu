@@ -1,0 +1,1008 @@
+// liblcba.so — C-ABI (include/lcba.h) over the sm_100a kernels.  Host side: handle,
+// device memory, ingest, the trust-region driver loop (kernel sequencing only: all
+// arithmetic, including step acceptance, runs on the device) and NCCL plumbing.
+#include <dlfcn.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "control.cuh"
+#include "dense.cuh"
+#include "eval.cuh"
+#include "ingest.cuh"
+#include "linearize.cuh"
+#include "schur.cuh"
+
+using namespace lcba;
+
+// ------------------------------------------------------------------------------ NCCL (dlopen)
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static const int NCCL_FLOAT64 = 8, NCCL_SUM = 0, NCCL_MAX = 2, NCCL_INT64 = 4;
+
+static bool nccl_load(std::string& err) {
+  if (g_nccl.lib) return true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.lib) break;
+  }
+  if (!g_nccl.lib) { err = std::string("dlopen libnccl.so.2 failed: ") + dlerror(); return false; }
+#define LOADSYM(field, sym)                                                           \
+  *(void**)(&g_nccl.field) = dlsym(g_nccl.lib, sym);                                  \
+  if (!g_nccl.field) { err = std::string("missing NCCL symbol ") + sym; g_nccl.lib = nullptr; return false; }
+  LOADSYM(GetUniqueId, "ncclGetUniqueId")
+  LOADSYM(CommInitRank, "ncclCommInitRank")
+  LOADSYM(AllReduce, "ncclAllReduce")
+  LOADSYM(CommDestroy, "ncclCommDestroy")
+  LOADSYM(GetErrorString, "ncclGetErrorString")
+#undef LOADSYM
+  return true;
+}
+
+// ------------------------------------------------------------------------------ handle
+struct lcba_handle {
+  int device = 0;
+  int sm_count = SM_COUNT_B200;
+  size_t smem_optin = 227 * 1024;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  std::vector<void*> allocs;
+
+  // problem (this rank's shard)
+  bool have_problem = false;
+  int C = 0;
+  long long P = 0, N = 0, P_total = 0;
+  int kmax = 0, B = 0;
+  long long nbins = 0;
+  double *d_cams[2] = {nullptr, nullptr}, *d_pts[2] = {nullptr, nullptr}, *d_tab[2] = {nullptr, nullptr};
+  int cur = 0;
+  double2* d_uv = nullptr;
+  double* d_w = nullptr;
+  uint8_t* d_cam = nullptr;
+  int32_t* d_pt = nullptr;
+  int32_t* d_perm = nullptr;
+  uint32_t* d_obs_start = nullptr;
+  unsigned long long* d_mask = nullptr;
+  // solver state
+  double *d_Vg = nullptr, *d_scl_p = nullptr, *d_gt_p = nullptr, *d_Lz = nullptr, *d_gn_p = nullptr;
+  double *d_camsum = nullptr, *d_scl_c = nullptr, *d_gt_c = nullptr, *d_g_c = nullptr, *d_pc = nullptr;
+  double *d_campart = nullptr, *d_part = nullptr, *d_red = nullptr, *d_coef = nullptr;
+  double *d_S = nullptr, *d_Lf = nullptr, *d_rhs = nullptr, *d_Sred = nullptr, *d_Spart = nullptr;
+  int* d_fail = nullptr;
+  Ctl* d_ctl = nullptr;
+  Ctl* h_ctl = nullptr;   // pinned
+  int lin_grid = 0, obs_grid = 0, pt_grid = 0;
+  SchurPlan plan;
+  SchurKind* d_kinds = nullptr;
+  SchurHw* d_hws = nullptr;
+  // outputs on demand
+  double2* d_rout = nullptr;
+  double *d_Jc = nullptr, *d_Jp = nullptr;
+  // trace / profile
+  std::vector<lcba_trace_row> trace;
+  bool prof_on = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::map<std::string, std::pair<long long, double>> prof;
+  long long launches = 0;
+  // comm
+  ncclComm_t comm = nullptr;
+  int rank = 0, nranks = 1;
+};
+
+static std::string g_last_error;
+static void set_error(lcba_t* h, const std::string& s) {
+  if (h) h->err = s;
+  g_last_error = s;
+}
+
+template <typename T>
+static int dev_alloc(lcba_t* h, T** p, size_t count) {
+  *p = nullptr;
+  if (count == 0) count = 1;
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, count * sizeof(T));
+  if (e != cudaSuccess) {
+    set_error(h, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    return LCBA_E_CUDA;
+  }
+  h->allocs.push_back(q);
+  *p = (T*)q;
+  return LCBA_OK;
+}
+
+static void dev_free_all(lcba_t* h) {
+  for (void* p : h->allocs) cudaFree(p);
+  h->allocs.clear();
+}
+
+#define KL(h, name, ...)                                              \
+  do {                                                                \
+    if ((h)->prof_on) cudaEventRecord((h)->ev0, (h)->stream);         \
+    __VA_ARGS__;                                                      \
+    (h)->launches++;                                                  \
+    if ((h)->prof_on) {                                               \
+      cudaEventRecord((h)->ev1, (h)->stream);                         \
+      cudaEventSynchronize((h)->ev1);                                 \
+      float ms_ = 0;                                                  \
+      cudaEventElapsedTime(&ms_, (h)->ev0, (h)->ev1);                 \
+      auto& pr_ = (h)->prof[name];                                    \
+      pr_.first++;                                                    \
+      pr_.second += ms_;                                              \
+    }                                                                 \
+  } while (0)
+
+static int check_launch(lcba_t* h, const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error(h, std::string(what) + ": " + cudaGetErrorString(e));
+    return LCBA_E_CUDA;
+  }
+  return LCBA_OK;
+}
+
+static int allreduce(lcba_t* h, double* p, size_t n, int op) {
+  if (!h->comm) return LCBA_OK;
+  int rc = g_nccl.AllReduce(p, p, n, NCCL_FLOAT64, op, h->comm, h->stream);
+  if (rc != 0) {
+    set_error(h, std::string("ncclAllReduce: ") + g_nccl.GetErrorString(rc));
+    return LCBA_E_NCCL;
+  }
+  return LCBA_OK;
+}
+
+// ------------------------------------------------------------------------------ lifecycle
+extern "C" int lcba_version(void) { return LCBA_VERSION; }
+
+extern "C" const char* lcba_last_error(const lcba_t* h) {
+  return h ? h->err.c_str() : g_last_error.c_str();
+}
+
+extern "C" void lcba_default_options(lcba_options* o) {
+  if (!o) return;
+  memset(o, 0, sizeof(*o));
+  o->ftol = 1e-8;   // scipy default; PySBA.bundleAdjust passes 1e-4 (pySBA.py:132)
+  o->xtol = 1e-8;
+  o->gtol = 1e-8;
+  o->max_nfev = 0;
+  o->verbose = 0;
+  o->profile = 0;
+}
+
+extern "C" int lcba_create(lcba_t** out, int device) {
+  if (!out) { set_error(nullptr, "lcba_create: out is NULL"); return LCBA_E_ARG; }
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    set_error(nullptr, std::string("no CUDA device (the engine has no CPU fallback): ") +
+                           (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0"));
+    return LCBA_E_CUDA;
+  }
+  lcba_t* h = new lcba_handle();
+  if (device < 0) cudaGetDevice(&device);
+  h->device = device;
+  if ((e = cudaSetDevice(device)) != cudaSuccess) {
+    set_error(nullptr, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    delete h;
+    return LCBA_E_CUDA;
+  }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  h->sm_count = prop.multiProcessorCount;
+  h->smem_optin = prop.sharedMemPerBlockOptin;
+  cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  cudaEventCreate(&h->ev0);
+  cudaEventCreate(&h->ev1);
+  cudaMallocHost((void**)&h->h_ctl, sizeof(Ctl));
+  // opt in to large dynamic shared memory
+  const int big = (int)h->smem_optin;
+  cudaFuncSetAttribute(k_linearize, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  cudaFuncSetAttribute(k_backsub, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  cudaFuncSetAttribute(k_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  cudaFuncSetAttribute(k_residual, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  cudaFuncSetAttribute(k_jdot, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  cudaFuncSetAttribute(k_jacobian_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  if ((e = cudaGetLastError()) != cudaSuccess) {
+    set_error(nullptr, std::string("lcba_create: ") + cudaGetErrorString(e));
+    delete h;
+    return LCBA_E_CUDA;
+  }
+  *out = h;
+  return LCBA_OK;
+}
+
+extern "C" void lcba_destroy(lcba_t* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  dev_free_all(h);
+  if (h->h_ctl) cudaFreeHost(h->h_ctl);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+// ------------------------------------------------------------------------------ ingest
+static inline unsigned nblk(long long n, int t) { return (unsigned)std::max<long long>(1, (n + t - 1) / t); }
+
+extern "C" int lcba_set_problem(lcba_t* h, int32_t C, int64_t P, int64_t N, const double* cams,
+                                const double* pts, const double* obs_uv, const int64_t* cam_idx,
+                                const int64_t* pt_idx, const double* weights) {
+  if (!h) return LCBA_E_ARG;
+  if (C <= 0 || P <= 0 || N <= 0 || !cams || !pts || !obs_uv || !cam_idx || !pt_idx) {
+    set_error(h, "lcba_set_problem: null pointer or non-positive size");
+    return LCBA_E_ARG;
+  }
+  if (C > LCBA_MAX_CAMERAS) {
+    set_error(h, "lcba_set_problem: more than 64 cameras is not supported");
+    return LCBA_E_UNSUPPORTED;
+  }
+  if (N >= (1LL << 31) || P >= (1LL << 31) / 3) {
+    set_error(h, "lcba_set_problem: shard too large for 32-bit indices; shard by point");
+    return LCBA_E_UNSUPPORTED;
+  }
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  dev_free_all(h);
+  h->have_problem = false;
+  h->d_rout = nullptr; h->d_Jc = nullptr; h->d_Jp = nullptr;
+  h->C = C; h->P = P; h->N = N; h->P_total = P; h->cur = 0;
+  cudaStream_t st = h->stream;
+
+  for (int i = 0; i < 2; ++i) {
+    LCBA_TRY(dev_alloc(h, &h->d_cams[i], (size_t)C * NCP));
+    LCBA_TRY(dev_alloc(h, &h->d_pts[i], (size_t)P * 3));
+    LCBA_TRY(dev_alloc(h, &h->d_tab[i], (size_t)C * CAMTAB));
+  }
+  LCBA_TRY(dev_alloc(h, &h->d_uv, (size_t)N));
+  if (weights) LCBA_TRY(dev_alloc(h, &h->d_w, (size_t)N)); else h->d_w = nullptr;
+  LCBA_TRY(dev_alloc(h, &h->d_cam, (size_t)N));
+  LCBA_TRY(dev_alloc(h, &h->d_pt, (size_t)N));
+  LCBA_TRY(dev_alloc(h, &h->d_obs_start, (size_t)P + 1));
+  LCBA_TRY(dev_alloc(h, &h->d_mask, (size_t)P));
+
+  // temporaries (freed at the end of ingest)
+  long long *t_cam = nullptr, *t_pt = nullptr;
+  unsigned long long *t_keys = nullptr, *t_keys2 = nullptr;
+  double2* t_uv = nullptr;
+  double* t_w = nullptr;
+  int32_t *t_iota = nullptr, *t_perm = nullptr;
+  int* d_flags = nullptr;
+  void* t_cub = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(t_cam); cudaFree(t_pt); cudaFree(t_keys); cudaFree(t_keys2); cudaFree(t_uv);
+    cudaFree(t_w); cudaFree(t_iota); cudaFree(t_cub); cudaFree(d_flags);
+  };
+#define ING(call)                                                                   \
+  do {                                                                              \
+    cudaError_t e_ = (call);                                                        \
+    if (e_ != cudaSuccess) {                                                        \
+      set_error(h, std::string(#call) + ": " + cudaGetErrorString(e_));             \
+      cleanup();                                                                    \
+      return LCBA_E_CUDA;                                                           \
+    }                                                                               \
+  } while (0)
+  ING(cudaMalloc(&t_cam, N * 8));
+  ING(cudaMalloc(&t_pt, N * 8));
+  ING(cudaMalloc(&t_keys, N * 8));
+  ING(cudaMalloc(&t_uv, N * 16));
+  if (weights) ING(cudaMalloc(&t_w, N * 8));
+  ING(cudaMalloc(&d_flags, 2 * sizeof(int)));
+  ING(cudaMemsetAsync(d_flags, 0, 2 * sizeof(int), st));
+  ING(cudaMemcpyAsync(t_cam, cam_idx, N * 8, cudaMemcpyHostToDevice, st));
+  ING(cudaMemcpyAsync(t_pt, pt_idx, N * 8, cudaMemcpyHostToDevice, st));
+  ING(cudaMemcpyAsync(t_uv, obs_uv, N * 16, cudaMemcpyHostToDevice, st));
+  if (weights) ING(cudaMemcpyAsync(t_w, weights, N * 8, cudaMemcpyHostToDevice, st));
+  ING(cudaMemcpyAsync(h->d_cams[0], cams, (size_t)C * NCP * 8, cudaMemcpyHostToDevice, st));
+  ING(cudaMemcpyAsync(h->d_pts[0], pts, (size_t)P * 3 * 8, cudaMemcpyHostToDevice, st));
+  k_make_keys<<<nblk(N, 256), 256, 0, st>>>(t_cam, t_pt, N, C, P, t_keys, d_flags);
+  h->launches++;
+  int flags[2] = {0, 0};
+  ING(cudaMemcpyAsync(flags, d_flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+  ING(cudaStreamSynchronize(st));
+  if (flags[0] & 1) {
+    set_error(h, "lcba_set_problem: camera or point index out of range");
+    cleanup();
+    return LCBA_E_ARG;
+  }
+  const unsigned long long* keys_sorted = t_keys;
+  h->d_perm = nullptr;
+  if (flags[0] & 2) {
+    // unsorted input: radix sort by (point, camera), remember the permutation
+    ING(cudaMalloc(&t_keys2, N * 8));
+    ING(cudaMalloc(&t_iota, N * 4));
+    LCBA_TRY(dev_alloc(h, &h->d_perm, (size_t)N));
+    k_iota<<<nblk(N, 256), 256, 0, st>>>(t_iota, N);
+    h->launches++;
+    size_t cub_bytes = 0;
+    int end_bit = 8;
+    while ((1LL << (end_bit - 8)) < P && end_bit < 64) ++end_bit;
+    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, t_keys, t_keys2, t_iota, h->d_perm,
+                                    (int)N, 0, end_bit, st);
+    ING(cudaMalloc(&t_cub, cub_bytes));
+    ING(cub::DeviceRadixSort::SortPairs(t_cub, cub_bytes, t_keys, t_keys2, t_iota, h->d_perm,
+                                        (int)N, 0, end_bit, st));
+    h->launches += 8;
+    keys_sorted = t_keys2;
+  }
+  k_narrow_gather<<<nblk(N, 256), 256, 0, st>>>(keys_sorted, h->d_perm, t_uv, t_w, N, h->d_cam,
+                                               h->d_pt, h->d_uv, h->d_w, d_flags);
+  k_obs_start<<<nblk(N + 1, 256), 256, 0, st>>>(h->d_pt, N, P, h->d_obs_start);
+  k_point_masks<<<nblk(P, 256), 256, 0, st>>>(h->d_cam, h->d_obs_start, P, h->d_mask, d_flags + 1);
+  h->launches += 3;
+  ING(cudaMemcpyAsync(flags, d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  ING(cudaStreamSynchronize(st));
+  ING(cudaGetLastError());
+  cleanup();
+#undef ING
+  if (flags[0] & 4) {
+    set_error(h, "lcba_set_problem: duplicate (camera, point) observation is not supported");
+    return LCBA_E_UNSUPPORTED;
+  }
+  h->kmax = flags[1];
+  h->B = LIN_THREADS - h->kmax;
+  if (h->B < 32) { set_error(h, "lcba_set_problem: too many observations per point"); return LCBA_E_UNSUPPORTED; }
+  h->nbins = N / h->B + 1;
+
+  // solver buffers
+  const int n = C * NCP;
+  LCBA_TRY(dev_alloc(h, &h->d_Vg, (size_t)P * 9));
+  LCBA_TRY(dev_alloc(h, &h->d_scl_p, (size_t)P * 3));
+  LCBA_TRY(dev_alloc(h, &h->d_gt_p, (size_t)P * 3));
+  LCBA_TRY(dev_alloc(h, &h->d_Lz, (size_t)P * 9));
+  LCBA_TRY(dev_alloc(h, &h->d_gn_p, (size_t)P * 3));
+  LCBA_TRY(dev_alloc(h, &h->d_camsum, (size_t)C * CAMSUM + 1));
+  LCBA_TRY(dev_alloc(h, &h->d_scl_c, (size_t)n));
+  LCBA_TRY(dev_alloc(h, &h->d_gt_c, (size_t)n));
+  LCBA_TRY(dev_alloc(h, &h->d_g_c, (size_t)n));
+  LCBA_TRY(dev_alloc(h, &h->d_pc, (size_t)n));
+  LCBA_TRY(dev_alloc(h, &h->d_S, (size_t)n * n));
+  LCBA_TRY(dev_alloc(h, &h->d_Lf, (size_t)n * n));
+  LCBA_TRY(dev_alloc(h, &h->d_rhs, (size_t)n));
+  LCBA_TRY(dev_alloc(h, &h->d_red, 64));
+  LCBA_TRY(dev_alloc(h, &h->d_coef, 2));
+  LCBA_TRY(dev_alloc(h, &h->d_fail, 1));
+  LCBA_TRY(dev_alloc(h, &h->d_ctl, 1));
+  // grids: persistent-style, a multiple of the SM count
+  const size_t lin_smem = linearize_smem_doubles(C) * 8;
+  const int lin_per_sm = std::max(1, (int)std::min<size_t>(4, h->smem_optin / (lin_smem + 1024)));
+  h->lin_grid = (int)std::min<long long>(h->nbins, (long long)h->sm_count * lin_per_sm);
+  h->obs_grid = (int)std::min<long long>(nblk(N, 256), (long long)h->sm_count * 8);
+  h->pt_grid = (int)std::min<long long>(nblk(P, 256), (long long)h->sm_count * 8);
+  const int max_grid = std::max(std::max(h->lin_grid, h->obs_grid), h->pt_grid);
+  LCBA_TRY(dev_alloc(h, &h->d_campart, (size_t)h->lin_grid * C * CAMSUM));
+  LCBA_TRY(dev_alloc(h, &h->d_part, (size_t)max_grid * 16));
+  // Schur plan
+  h->plan = make_schur_plan(C, h->sm_count, h->smem_optin - 2048);
+  LCBA_TRY(dev_alloc(h, &h->d_kinds, h->plan.kinds.size()));
+  LCBA_TRY(dev_alloc(h, &h->d_hws, h->plan.hws.size()));
+  LCBA_CUDA(h, cudaMemcpyAsync(h->d_kinds, h->plan.kinds.data(), h->plan.kinds.size() * sizeof(SchurKind),
+                               cudaMemcpyHostToDevice, st));
+  LCBA_CUDA(h, cudaMemcpyAsync(h->d_hws, h->plan.hws.data(), h->plan.hws.size() * sizeof(SchurHw),
+                               cudaMemcpyHostToDevice, st));
+  LCBA_TRY(dev_alloc(h, &h->d_Sred, h->plan.part_stride));
+  LCBA_TRY(dev_alloc(h, &h->d_Spart, h->plan.part_stride * h->plan.nslices));
+  LCBA_CUDA(h, cudaStreamSynchronize(st));
+  h->have_problem = true;
+  return LCBA_OK;
+}
+
+extern "C" int lcba_set_params(lcba_t* h, const double* cams, const double* pts) {
+  if (!h || !h->have_problem) { set_error(h, "lcba_set_params: no problem set"); return LCBA_E_STATE; }
+  if (!cams || !pts) { set_error(h, "lcba_set_params: null pointer"); return LCBA_E_ARG; }
+  cudaSetDevice(h->device);
+  LCBA_CUDA(h, cudaMemcpyAsync(h->d_cams[h->cur], cams, (size_t)h->C * NCP * 8, cudaMemcpyHostToDevice, h->stream));
+  LCBA_CUDA(h, cudaMemcpyAsync(h->d_pts[h->cur], pts, (size_t)h->P * 3 * 8, cudaMemcpyHostToDevice, h->stream));
+  LCBA_CUDA(h, cudaStreamSynchronize(h->stream));
+  return LCBA_OK;
+}
+
+extern "C" int lcba_get_params(lcba_t* h, double* cams_out, double* pts_out) {
+  if (!h || !h->have_problem) { set_error(h, "lcba_get_params: no problem set"); return LCBA_E_STATE; }
+  cudaSetDevice(h->device);
+  if (cams_out)
+    LCBA_CUDA(h, cudaMemcpyAsync(cams_out, h->d_cams[h->cur], (size_t)h->C * NCP * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (pts_out)
+    LCBA_CUDA(h, cudaMemcpyAsync(pts_out, h->d_pts[h->cur], (size_t)h->P * 3 * 8, cudaMemcpyDeviceToHost, h->stream));
+  LCBA_CUDA(h, cudaStreamSynchronize(h->stream));
+  return LCBA_OK;
+}
+
+// ------------------------------------------------------------------------------ row-wise API
+static int rows_call(lcba_t* h, int64_t M, const double* a, int acols, const double* b, int bcols,
+                     double* out, int ocols, int which) {
+  if (!h) return LCBA_E_ARG;
+  if (M < 0 || (M > 0 && (!a || !b || !out))) { set_error(h, "null pointer or negative size"); return LCBA_E_ARG; }
+  if (M == 0) return LCBA_OK;
+  cudaSetDevice(h->device);
+  double *da = nullptr, *db = nullptr, *dout = nullptr;
+  cudaError_t e;
+  auto fail = [&](const char* what) {
+    set_error(h, std::string(what) + ": " + cudaGetErrorString(e));
+    cudaFree(da); cudaFree(db); cudaFree(dout);
+    return LCBA_E_CUDA;
+  };
+  if ((e = cudaMalloc(&da, (size_t)M * acols * 8)) != cudaSuccess) return fail("cudaMalloc");
+  if ((e = cudaMalloc(&db, (size_t)M * bcols * 8)) != cudaSuccess) return fail("cudaMalloc");
+  if ((e = cudaMalloc(&dout, (size_t)M * ocols * 8)) != cudaSuccess) return fail("cudaMalloc");
+  cudaMemcpyAsync(da, a, (size_t)M * acols * 8, cudaMemcpyHostToDevice, h->stream);
+  cudaMemcpyAsync(db, b, (size_t)M * bcols * 8, cudaMemcpyHostToDevice, h->stream);
+  if (which == 0) k_rotate_rows<<<nblk(M, 256), 256, 0, h->stream>>>(da, db, dout, M);
+  else k_project_rows<<<nblk(M, 256), 256, 0, h->stream>>>(da, db, dout, M);
+  h->launches++;
+  cudaMemcpyAsync(out, dout, (size_t)M * ocols * 8, cudaMemcpyDeviceToHost, h->stream);
+  e = cudaStreamSynchronize(h->stream);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) return fail("rows kernel");
+  cudaFree(da); cudaFree(db); cudaFree(dout);
+  return LCBA_OK;
+}
+
+extern "C" int lcba_rotate(lcba_t* h, int64_t M, const double* pts, const double* rot_vecs, double* out) {
+  return rows_call(h, M, pts, 3, rot_vecs, 3, out, 3, 0);
+}
+extern "C" int lcba_project(lcba_t* h, int64_t M, const double* pts, const double* cams_rows, double* out_uv) {
+  return rows_call(h, M, pts, 3, cams_rows, NCP, out_uv, 2, 1);
+}
+
+extern "C" int lcba_sparsity_indices(lcba_t* h, int32_t C, int64_t P, int64_t N, const int64_t* cam_idx,
+                                     const int64_t* pt_idx, int32_t* indices_out) {
+  if (!h) return LCBA_E_ARG;
+  if (C <= 0 || P <= 0 || N < 0 || (N > 0 && (!cam_idx || !pt_idx || !indices_out))) {
+    set_error(h, "lcba_sparsity_indices: bad argument");
+    return LCBA_E_ARG;
+  }
+  if ((long long)C * NCP + 3 * P >= (1LL << 31)) { set_error(h, "column index exceeds int32"); return LCBA_E_UNSUPPORTED; }
+  if (N == 0) return LCBA_OK;
+  cudaSetDevice(h->device);
+  long long *dc = nullptr, *dp = nullptr;
+  int32_t* dout = nullptr;
+  cudaError_t e = cudaMalloc(&dc, N * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&dp, N * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&dout, (size_t)N * 28 * 4);
+  if (e == cudaSuccess) {
+    cudaMemcpyAsync(dc, cam_idx, N * 8, cudaMemcpyHostToDevice, h->stream);
+    cudaMemcpyAsync(dp, pt_idx, N * 8, cudaMemcpyHostToDevice, h->stream);
+    k_sparsity_indices<<<nblk(N * 28, 256), 256, 0, h->stream>>>(dc, dp, N, C, dout);
+    h->launches++;
+    cudaMemcpyAsync(indices_out, dout, (size_t)N * 28 * 4, cudaMemcpyDeviceToHost, h->stream);
+    e = cudaStreamSynchronize(h->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+  }
+  cudaFree(dc); cudaFree(dp); cudaFree(dout);
+  if (e != cudaSuccess) { set_error(h, std::string("lcba_sparsity_indices: ") + cudaGetErrorString(e)); return LCBA_E_CUDA; }
+  return LCBA_OK;
+}
+
+// ------------------------------------------------------------------------------ evaluation
+static int build_tables(lcba_t* h, int which) {
+  KL(h, "cam_tables", k_cam_tables<<<1, 64, 0, h->stream>>>(h->d_cams[which], h->d_tab[which], h->C));
+  return LCBA_OK;
+}
+
+// sum r^2 of buffer set `which` -> d_red[0] (all-reduced); optional residual output
+static int run_residual(lcba_t* h, int which, double2* r_out) {
+  const size_t smem = (size_t)h->C * CAMTAB * 8;
+  KL(h, "residual", k_residual<<<h->obs_grid, 256, smem, h->stream>>>(
+        h->d_tab[which], h->d_pts[which], h->d_uv, h->d_cam, h->d_pt, h->d_w, h->d_perm, h->N, h->C,
+        r_out, h->d_part));
+  KL(h, "reduce", k_reduce_scalars<<<1, 256, 0, h->stream>>>(h->d_part, h->obs_grid, 1, h->d_red, 1));
+  return allreduce(h, h->d_red, 1, NCCL_SUM);
+}
+
+static int upload_x_to(lcba_t* h, const double* x, int which) {
+  LCBA_CUDA(h, cudaMemcpyAsync(h->d_cams[which], x, (size_t)h->C * NCP * 8, cudaMemcpyHostToDevice, h->stream));
+  LCBA_CUDA(h, cudaMemcpyAsync(h->d_pts[which], x + (size_t)h->C * NCP, (size_t)h->P * 3 * 8,
+                               cudaMemcpyHostToDevice, h->stream));
+  return LCBA_OK;
+}
+
+extern "C" int lcba_residuals(lcba_t* h, const double* x_or_null, double* r_out, double* cost_out) {
+  if (!h || !h->have_problem) { set_error(h, "lcba_residuals: no problem set"); return LCBA_E_STATE; }
+  cudaSetDevice(h->device);
+  int which = h->cur;
+  if (x_or_null) { which = 1 - h->cur; LCBA_TRY(upload_x_to(h, x_or_null, which)); }
+  LCBA_TRY(build_tables(h, which));
+  if (r_out && !h->d_rout) LCBA_TRY(dev_alloc(h, &h->d_rout, (size_t)h->N));
+  LCBA_TRY(run_residual(h, which, r_out ? h->d_rout : nullptr));
+  double ss = 0;
+  LCBA_CUDA(h, cudaMemcpyAsync(&ss, h->d_red, 8, cudaMemcpyDeviceToHost, h->stream));
+  if (r_out) LCBA_CUDA(h, cudaMemcpyAsync(r_out, h->d_rout, (size_t)h->N * 16, cudaMemcpyDeviceToHost, h->stream));
+  LCBA_CUDA(h, cudaStreamSynchronize(h->stream));
+  LCBA_TRY(check_launch(h, "lcba_residuals"));
+  if (cost_out) *cost_out = 0.5 * ss;
+  return LCBA_OK;
+}
+
+static int run_jacobian_blocks(lcba_t* h, int which) {
+  const size_t smem = ((size_t)((h->C * CAMTAB + 1) & ~1) + (size_t)(JB_THREADS / 32) * JB_LD * JB_STAGE) * 8;
+  const long long groups = (h->N + 31) / 32;
+  const int grid = (int)std::min<long long>((groups + 7) / 8, (long long)h->sm_count * 4);
+  KL(h, "jacobian_blocks", k_jacobian_blocks<<<grid, JB_THREADS, smem, h->stream>>>(
+        h->d_tab[which], h->d_pts[which], h->d_uv, h->d_cam, h->d_pt, h->d_w, h->d_perm, h->N, h->C,
+        h->d_rout, h->d_Jc, h->d_Jp));
+  return LCBA_OK;
+}
+
+static int ensure_jac_buffers(lcba_t* h) {
+  if (!h->d_rout) LCBA_TRY(dev_alloc(h, &h->d_rout, (size_t)h->N));
+  if (!h->d_Jc) LCBA_TRY(dev_alloc(h, &h->d_Jc, (size_t)h->N * 22));
+  if (!h->d_Jp) LCBA_TRY(dev_alloc(h, &h->d_Jp, (size_t)h->N * 6));
+  return LCBA_OK;
+}
+
+extern "C" int lcba_jacobian_blocks(lcba_t* h, const double* x_or_null, double* Jc, double* Jp) {
+  if (!h || !h->have_problem) { set_error(h, "lcba_jacobian_blocks: no problem set"); return LCBA_E_STATE; }
+  cudaSetDevice(h->device);
+  int which = h->cur;
+  if (x_or_null) { which = 1 - h->cur; LCBA_TRY(upload_x_to(h, x_or_null, which)); }
+  LCBA_TRY(build_tables(h, which));
+  LCBA_TRY(ensure_jac_buffers(h));
+  LCBA_TRY(run_jacobian_blocks(h, which));
+  if (Jc) LCBA_CUDA(h, cudaMemcpyAsync(Jc, h->d_Jc, (size_t)h->N * 22 * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (Jp) LCBA_CUDA(h, cudaMemcpyAsync(Jp, h->d_Jp, (size_t)h->N * 6 * 8, cudaMemcpyDeviceToHost, h->stream));
+  LCBA_CUDA(h, cudaStreamSynchronize(h->stream));
+  return check_launch(h, "lcba_jacobian_blocks");
+}
+
+// ------------------------------------------------------------------------------ solver passes
+static int pass_linearize(lcba_t* h, int first) {
+  const int C = h->C, w = h->cur;
+  LCBA_TRY(build_tables(h, w));
+  const size_t smem = linearize_smem_doubles(C) * 8;
+  KL(h, "linearize", k_linearize<<<h->lin_grid, LIN_THREADS, smem, h->stream>>>(
+        h->d_tab[w], h->d_pts[w], h->d_uv, h->d_cam, h->d_pt, h->d_w, h->d_obs_start, h->P, h->nbins,
+        h->B, C, h->d_Vg, h->d_campart, h->d_part));
+  KL(h, "reduce", k_reduce_cols<<<nblk(C * CAMSUM, 128), 128, 0, h->stream>>>(
+        h->d_campart, h->lin_grid, C * CAMSUM, h->d_camsum));
+  KL(h, "reduce", k_reduce_scalars<<<1, 256, 0, h->stream>>>(h->d_part, h->lin_grid, 1,
+                                                             h->d_camsum + C * CAMSUM, 1));
+  LCBA_TRY(allreduce(h, h->d_camsum, (size_t)C * CAMSUM + 1, NCCL_SUM));
+  KL(h, "ctl", k_ctl_lin<<<1, 256, 0, h->stream>>>(h->d_camsum, h->d_cams[w], h->d_scl_c, h->d_gt_c,
+                                                   h->d_g_c, C, h->d_ctl, first));
+  KL(h, "point_prep", k_point_prep<<<h->pt_grid, 256, 0, h->stream>>>(
+        h->d_Vg, h->d_pts[w], h->d_scl_p, h->d_gt_p, h->P, first, h->d_part));
+  KL(h, "reduce", k_reduce_scalars<<<PP_K, 256, 0, h->stream>>>(h->d_part, h->pt_grid, PP_K, h->d_red, 3));
+  LCBA_TRY(allreduce(h, h->d_red, 3, NCCL_SUM));
+  LCBA_TRY(allreduce(h, h->d_red + 3, 1, NCCL_MAX));
+  KL(h, "ctl", k_ctl_lin2<<<1, 1, 0, h->stream>>>(h->d_red, h->d_ctl, first));
+  return check_launch(h, "linearize pass");
+}
+
+static int pass_jdot(lcba_t* h) {
+  const int C = h->C, w = h->cur;
+  const size_t smem = ((size_t)C * CAMTAB + (size_t)C * NCP) * 8;
+  KL(h, "jdot", k_jdot<<<h->obs_grid, 256, smem, h->stream>>>(
+        h->d_tab[w], h->d_pts[w], h->d_cam, h->d_pt, h->d_w, h->d_gt_c, h->d_gt_p, h->N, C, h->d_part));
+  KL(h, "reduce", k_reduce_scalars<<<1, 256, 0, h->stream>>>(h->d_part, h->obs_grid, 1, h->d_red, 1));
+  LCBA_TRY(allreduce(h, h->d_red, 1, NCCL_SUM));
+  KL(h, "ctl", k_ctl_reg<<<1, 1, 0, h->stream>>>(h->d_red, h->d_ctl));
+  return check_launch(h, "jdot pass");
+}
+
+__global__ void k_point_factor_ctl(const double* Vg, const double* scl, const Ctl* ctl, long long P,
+                                   double* Lz);
+__global__ void k_assemble_S_ctl(const double* red, int C, int npairs, const double* camsum,
+                                 const double* scl_c, const Ctl* ctl, double* S, double* rhs);
+
+static int pass_schur(lcba_t* h, const double* lam_host_or_null) {
+  const int C = h->C, w = h->cur, n = C * NCP;
+  const SchurPlan& pl = h->plan;
+  if (lam_host_or_null) {
+    KL(h, "point_factor", k_point_factor<<<nblk(h->P, 256), 256, 0, h->stream>>>(
+          h->d_Vg, h->d_scl_p, *lam_host_or_null, h->P, h->d_Lz));
+  } else {
+    KL(h, "point_factor", k_point_factor_ctl<<<nblk(h->P, 256), 256, 0, h->stream>>>(
+          h->d_Vg, h->d_scl_p, h->d_ctl, h->P, h->d_Lz));
+  }
+  dim3 grid(pl.nslices, pl.nkinds);
+  KL(h, "schur", k_schur<<<grid, pl.max_threads, pl.smem_bytes, h->stream>>>(
+        h->d_tab[w], h->d_pts[w], h->d_w, h->d_obs_start, h->d_mask, h->d_Lz, h->P, h->N, C, h->d_kinds,
+        h->d_hws, pl.pc, pl.nslices, pl.part_stride, pl.npairs, h->d_Spart));
+  KL(h, "schur_reduce", k_reduce_cols<<<nblk((long long)pl.part_stride, 256), 256, 0, h->stream>>>(
+        h->d_Spart, pl.nslices, (int)pl.part_stride, h->d_Sred));
+  LCBA_TRY(allreduce(h, h->d_Sred, pl.part_stride, NCCL_SUM));
+  if (lam_host_or_null) {
+    KL(h, "assemble", k_assemble_S<<<nblk((long long)n * n, 256), 256, 0, h->stream>>>(
+          h->d_Sred, C, pl.npairs, h->d_camsum, h->d_scl_c, *lam_host_or_null, h->d_S, h->d_rhs));
+  } else {
+    KL(h, "assemble", k_assemble_S_ctl<<<nblk((long long)n * n, 256), 256, 0, h->stream>>>(
+          h->d_Sred, C, pl.npairs, h->d_camsum, h->d_scl_c, h->d_ctl, h->d_S, h->d_rhs));
+  }
+  return check_launch(h, "schur pass");
+}
+
+// lambda read from the device control block (no host round trip)
+__global__ void __launch_bounds__(256)
+k_point_factor_ctl(const double* __restrict__ Vg, const double* __restrict__ scl,
+                   const Ctl* __restrict__ ctl, long long P, double* __restrict__ Lz) {
+  // same arithmetic as k_point_factor; kept as a thin wrapper through a device call
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const double lam = ctl->reg_term;
+  const double* v = Vg + p * 9;
+  const double s0 = scl[3 * p], s1 = scl[3 * p + 1], s2 = scl[3 * p + 2];
+  const double v00 = fma(lam * s0, s0, v[0]), v11 = fma(lam * s1, s1, v[3]), v22 = fma(lam * s2, s2, v[5]);
+  const double v01 = v[1], v02 = v[2], v12 = v[4];
+  const double tiny = 1e-300;
+  const double l00 = sqrt(fmax(v00, tiny));
+  const double i00 = 1.0 / l00;
+  const double l10 = v01 * i00, l20 = v02 * i00;
+  const double d11 = v11 - l10 * l10;
+  const double l11 = sqrt(fmax(d11, fmax(1e-14 * v11, tiny)));
+  const double i11 = 1.0 / l11;
+  const double l21 = (v12 - l20 * l10) * i11;
+  const double d22 = v22 - l20 * l20 - l21 * l21;
+  const double l22 = sqrt(fmax(d22, fmax(1e-14 * v22, tiny)));
+  const double i22 = 1.0 / l22;
+  const double i10 = -l10 * i00 * i11;
+  const double i21 = -l21 * i11 * i22;
+  const double i20 = -(l20 * i00 + l21 * i10) * i22;
+  double* o = Lz + p * 9;
+  o[0] = i00; o[1] = i10; o[2] = i11; o[3] = i20; o[4] = i21; o[5] = i22;
+  const double g0 = v[6], g1 = v[7], g2 = v[8];
+  o[6] = i00 * g0;
+  o[7] = fma(i10, g0, i11 * g1);
+  o[8] = fma(i20, g0, fma(i21, g1, i22 * g2));
+}
+
+__global__ void k_assemble_S_ctl(const double* __restrict__ red, int C, int npairs,
+                                 const double* __restrict__ camsum, const double* __restrict__ scl_c,
+                                 const Ctl* __restrict__ ctl, double* __restrict__ S,
+                                 double* __restrict__ rhs) {
+  const double lam = ctl->reg_term;
+  const int n = C * NCP;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)n * n) return;
+  const int r = (int)(idx / n), c = (int)(idx % n);
+  const int hi = max(r, c), lo = min(r, c);
+  const int j = hi / NCP, a = hi % NCP, k = lo / NCP, b = lo % NCP;
+  double v;
+  if (j == k) v = red[(size_t)(j * (j + 1) / 2 + j) * 121 + (r % NCP) * NCP + (c % NCP)];
+  else v = red[(size_t)(j * (j + 1) / 2 + k) * 121 + a * NCP + b];
+  if (r == c) {
+    const double s = scl_c[r];
+    v = fma(lam * s, s, v);
+    rhs[r] = camsum[(r / NCP) * 22 + (r % NCP)] + red[(size_t)npairs * 121 + r];
+  }
+  S[idx] = v;
+}
+
+// Cholesky of S + mu*Dc^2, solve for the camera step
+static int pass_camera_solve(lcba_t* h, double mu) {
+  const int n = h->C * NCP;
+  LCBA_CUDA(h, cudaMemsetAsync(h->d_fail, 0, sizeof(int), h->stream));
+  KL(h, "chol_copy", k_copy_damped<<<nblk((long long)n * n, 256), 256, 0, h->stream>>>(
+        h->d_S, n, mu, h->d_scl_c, h->d_Lf));
+  for (int k = 0; k < n; k += CH_NB) {
+    KL(h, "chol_panel", k_chol_panel<<<1, 256, 0, h->stream>>>(h->d_Lf, n, k, h->d_fail));
+    const int rem = n - k - CH_NB;
+    if (rem > 0) {
+      const int nt = (rem + CH_NB - 1) / CH_NB;
+      KL(h, "chol_update", k_chol_update<<<dim3(nt, nt), 256, 0, h->stream>>>(h->d_Lf, n, k));
+    }
+  }
+  KL(h, "chol_solve", k_chol_solve<<<1, 256, (size_t)n * 8, h->stream>>>(h->d_Lf, n, h->d_rhs, h->d_pc));
+  return check_launch(h, "camera solve");
+}
+
+static int pass_backsub(lcba_t* h) {
+  const int C = h->C, w = h->cur;
+  const size_t smem = ((size_t)C * CAMTAB + 2 * (size_t)C * NCP + 2 * LIN_THREADS * 3) * 8;
+  KL(h, "backsub", k_backsub<<<h->lin_grid, LIN_THREADS, smem, h->stream>>>(
+        h->d_tab[w], h->d_pts[w], h->d_cam, h->d_pt, h->d_w, h->d_obs_start, h->P, h->nbins, h->B, C,
+        h->d_Vg, h->d_Lz, h->d_scl_p, h->d_gt_c, h->d_gt_p, h->d_pc, h->d_gn_p, h->d_part));
+  KL(h, "reduce", k_reduce_scalars<<<BS_K, 256, 0, h->stream>>>(h->d_part, h->lin_grid, BS_K, h->d_red, BS_K));
+  LCBA_TRY(allreduce(h, h->d_red, BS_K, NCCL_SUM));
+  KL(h, "ctl", k_ctl_sub<<<1, 256, 0, h->stream>>>(h->d_red, h->d_g_c, h->d_gt_c, h->d_pc, h->d_scl_c, C,
+                                                   h->d_ctl, h->d_fail, h->d_coef));
+  return check_launch(h, "backsub pass");
+}
+
+static int pass_trial(lcba_t* h) {
+  const int w = h->cur, t = 1 - h->cur;
+  const long long nc = (long long)h->C * NCP, np = h->P * 3;
+  KL(h, "make_trial", k_make_trial<<<1, 256, 0, h->stream>>>(h->d_cams[w], h->d_gt_c, h->d_pc, h->d_coef, nc,
+                                                             h->d_cams[t]));
+  KL(h, "make_trial", k_make_trial<<<h->pt_grid, 256, 0, h->stream>>>(h->d_pts[w], h->d_gt_p, h->d_gn_p,
+                                                                      h->d_coef, np, h->d_pts[t]));
+  LCBA_TRY(build_tables(h, t));
+  LCBA_TRY(run_residual(h, t, nullptr));
+  KL(h, "ctl", k_ctl_trial<<<1, 1, 0, h->stream>>>(h->d_red, h->d_ctl, h->d_coef));
+  return check_launch(h, "trial pass");
+}
+
+static int read_ctl(lcba_t* h) {
+  LCBA_CUDA(h, cudaMemcpyAsync(h->h_ctl, h->d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, h->stream));
+  LCBA_CUDA(h, cudaStreamSynchronize(h->stream));
+  return check_launch(h, "solver");
+}
+
+static void add_trace(lcba_t* h, long long it, long long nfev, double cost, double red, double step,
+                      double opt, double delta, double reg) {
+  if (h->trace.size() >= LCBA_MAX_TRACE) return;
+  lcba_trace_row r;
+  r.iteration = it; r.nfev = nfev; r.cost = cost; r.cost_reduction = red; r.step_norm = step;
+  r.optimality = opt; r.delta = delta; r.reg_term = reg;
+  h->trace.push_back(r);
+}
+
+extern "C" int lcba_solve(lcba_t* h, const lcba_options* opt_in, lcba_result* res) {
+  if (!h || !h->have_problem) { set_error(h, "lcba_solve: no problem set"); return LCBA_E_STATE; }
+  if (!res) { set_error(h, "lcba_solve: res is NULL"); return LCBA_E_ARG; }
+  lcba_options opt;
+  if (opt_in) opt = *opt_in; else lcba_default_options(&opt);
+  cudaSetDevice(h->device);
+  memset(res, 0, sizeof(*res));
+  h->trace.clear();
+  h->prof.clear();
+  h->prof_on = opt.profile != 0;
+  const long long n_total = (long long)h->C * NCP + 3 * h->P_total;
+  const long long max_nfev = opt.max_nfev > 0 ? opt.max_nfev : 100 * n_total;
+
+  cudaEvent_t t0, t1;
+  cudaEventCreate(&t0);
+  cudaEventCreate(&t1);
+  cudaEventRecord(t0, h->stream);
+
+  Ctl init;
+  memset(&init, 0, sizeof(init));
+  init.ftol = opt.ftol;
+  init.xtol = opt.xtol;
+  init.term = -1;
+  LCBA_CUDA(h, cudaMemcpyAsync(h->d_ctl, &init, sizeof(Ctl), cudaMemcpyHostToDevice, h->stream));
+
+  LCBA_TRY(pass_linearize(h, 1));
+  LCBA_TRY(read_ctl(h));
+  if (h->h_ctl->nonfinite) {
+    set_error(h, "Residuals are not finite in the initial point.");
+    cudaEventDestroy(t0); cudaEventDestroy(t1);
+    return LCBA_E_NONFINITE;
+  }
+  long long nfev = 1, njev = 1, iteration = 0;
+  int status = -1;
+  res->initial_cost = h->h_ctl->cost;
+  double cost = h->h_ctl->cost, g_norm = h->h_ctl->g_norm;
+  double step_norm = NAN, actual = NAN;
+  double last_reg = 0.0;
+  while (true) {
+    if (g_norm < opt.gtol) status = LCBA_STATUS_GTOL;
+    add_trace(h, iteration, nfev, cost, actual, step_norm, g_norm, h->h_ctl->Delta, last_reg);
+    if (status >= 0 || nfev >= max_nfev) break;
+
+    LCBA_TRY(pass_jdot(h));
+    LCBA_TRY(pass_schur(h, nullptr));
+    double mu = 0.0;
+    bool have_trial = false;
+    actual = -1.0;
+    int term = -1;
+    while (true) {   // Cholesky retry loop (extra camera damping on breakdown)
+      LCBA_TRY(pass_camera_solve(h, mu));
+      LCBA_TRY(pass_backsub(h));
+      LCBA_TRY(pass_trial(h));
+      LCBA_TRY(read_ctl(h));
+      if (h->h_ctl->retry) {
+        mu = std::max(std::max(10.0 * mu, 10.0 * h->h_ctl->reg_term), 1e-13);
+        if (mu > 1e6) {
+          set_error(h, "reduced camera system is not positive definite even with damping");
+          cudaEventDestroy(t0); cudaEventDestroy(t1);
+          return LCBA_E_NONFINITE;
+        }
+        continue;
+      }
+      have_trial = true;
+      break;
+    }
+    last_reg = h->h_ctl->reg_term;
+    // inner loop: trials until the cost decreases (trf.py:503-541)
+    while (true) {
+      if (have_trial) { nfev++; have_trial = false; }
+      const Ctl& c = *h->h_ctl;
+      const bool finite = (c.cost_new - c.cost_new == 0.0);
+      if (finite) {
+        actual = c.actual;
+        step_norm = c.step_norm;
+        term = c.term;
+        if (term >= 0) break;
+      }
+      if (finite && actual > 0.0) break;
+      if (nfev >= max_nfev) break;
+      LCBA_TRY(pass_trial(h));
+      LCBA_TRY(read_ctl(h));
+      have_trial = true;
+    }
+    if (term >= 0) status = term;
+    if (actual > 0.0) {
+      h->cur = 1 - h->cur;      // x <- x_new (buffers swap, tables included)
+      KL(h, "ctl", k_ctl_commit<<<1, 1, 0, h->stream>>>(h->d_ctl));
+      LCBA_TRY(pass_linearize(h, 0));
+      njev++;
+      LCBA_TRY(read_ctl(h));
+      cost = h->h_ctl->cost;
+      g_norm = h->h_ctl->g_norm;
+    } else {
+      step_norm = 0.0;
+      actual = 0.0;
+    }
+    iteration++;
+  }
+  if (status < 0) status = LCBA_STATUS_MAX_NFEV;
+  cudaEventRecord(t1, h->stream);
+  cudaEventSynchronize(t1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, t0, t1);
+  cudaEventDestroy(t0);
+  cudaEventDestroy(t1);
+  res->cost = cost;
+  res->optimality = g_norm;
+  res->nfev = nfev;
+  res->njev = njev;
+  res->iterations = iteration;
+  res->status = status;
+  res->n_trace = (int)h->trace.size();
+  res->solve_ms = ms;
+  h->prof_on = false;
+  return LCBA_OK;
+}
+
+extern "C" int lcba_get_trace(lcba_t* h, lcba_trace_row* rows, int32_t max_rows) {
+  if (!h || !rows) return LCBA_E_ARG;
+  const int n = std::min<int>(max_rows, (int)h->trace.size());
+  for (int i = 0; i < n; ++i) rows[i] = h->trace[i];
+  return n;
+}
+
+extern "C" int lcba_get_profile(lcba_t* h, lcba_kernel_stat* stats, int32_t max_stats, int32_t* n_out) {
+  if (!h || !n_out) return LCBA_E_ARG;
+  int i = 0;
+  for (auto& kv : h->prof) {
+    if (i >= max_stats) break;
+    if (stats) {
+      memset(&stats[i], 0, sizeof(stats[i]));
+      strncpy(stats[i].name, kv.first.c_str(), sizeof(stats[i].name) - 1);
+      stats[i].launches = kv.second.first;
+      stats[i].total_ms = kv.second.second;
+    }
+    ++i;
+  }
+  *n_out = i;
+  return LCBA_OK;
+}
+
+__global__ void k_extract_gp(const double* __restrict__ Vg, long long P, double* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < P * 3) out[i] = Vg[(i / 3) * 9 + 6 + (i % 3)];
+}
+
+extern "C" int lcba_get_grad(lcba_t* h, double* g_out) {
+  if (!h || !h->have_problem) { set_error(h, "lcba_get_grad: no problem set"); return LCBA_E_STATE; }
+  if (!g_out) return LCBA_E_ARG;
+  cudaSetDevice(h->device);
+  const size_t nc = (size_t)h->C * NCP;
+  KL(h, "extract", k_extract_gp<<<nblk(h->P * 3, 256), 256, 0, h->stream>>>(h->d_Vg, h->P, h->d_gn_p));
+  LCBA_CUDA(h, cudaMemcpyAsync(g_out, h->d_g_c, nc * 8, cudaMemcpyDeviceToHost, h->stream));
+  LCBA_CUDA(h, cudaMemcpyAsync(g_out + nc, h->d_gn_p, (size_t)h->P * 3 * 8, cudaMemcpyDeviceToHost, h->stream));
+  LCBA_CUDA(h, cudaStreamSynchronize(h->stream));
+  return check_launch(h, "lcba_get_grad");
+}
+
+__global__ void k_concat_scale(const double* __restrict__ scl_c, int nc, const double* __restrict__ scl_p,
+                               long long np, double* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nc) out[i] = scl_c[i];
+  else if (i < nc + np) out[i] = scl_p[i - nc];
+}
+
+extern "C" int lcba_linearize(lcba_t* h, double lam, double* S_out, double* rhs_out, double* grad_out,
+                              double* scale_inv_out, double* cost_out) {
+  if (!h || !h->have_problem) { set_error(h, "lcba_linearize: no problem set"); return LCBA_E_STATE; }
+  cudaSetDevice(h->device);
+  Ctl init;
+  memset(&init, 0, sizeof(init));
+  init.term = -1;
+  LCBA_CUDA(h, cudaMemcpyAsync(h->d_ctl, &init, sizeof(Ctl), cudaMemcpyHostToDevice, h->stream));
+  LCBA_TRY(pass_linearize(h, 1));
+  LCBA_TRY(pass_schur(h, &lam));
+  const int n = h->C * NCP;
+  if (S_out) LCBA_CUDA(h, cudaMemcpyAsync(S_out, h->d_S, (size_t)n * n * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (rhs_out) LCBA_CUDA(h, cudaMemcpyAsync(rhs_out, h->d_rhs, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
+  LCBA_TRY(read_ctl(h));
+  if (cost_out) *cost_out = h->h_ctl->cost;
+  if (grad_out) LCBA_TRY(lcba_get_grad(h, grad_out));
+  if (scale_inv_out) {
+    LCBA_CUDA(h, cudaMemcpyAsync(scale_inv_out, h->d_scl_c, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
+    LCBA_CUDA(h, cudaMemcpyAsync(scale_inv_out + n, h->d_scl_p, (size_t)h->P * 3 * 8, cudaMemcpyDeviceToHost, h->stream));
+    LCBA_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  return check_launch(h, "lcba_linearize");
+}
+
+extern "C" int lcba_time_device(lcba_t* h, int32_t what, int32_t reps, double* ms_out) {
+  if (!h || !h->have_problem) { set_error(h, "lcba_time_device: no problem set"); return LCBA_E_STATE; }
+  if (!ms_out || reps <= 0) return LCBA_E_ARG;
+  cudaSetDevice(h->device);
+  LCBA_TRY(build_tables(h, h->cur));
+  if (what == 1) LCBA_TRY(ensure_jac_buffers(h));
+  cudaEvent_t t0, t1;
+  cudaEventCreate(&t0);
+  cudaEventCreate(&t1);
+  int rc = LCBA_OK;
+  for (int r = -1; r < reps && rc == LCBA_OK; ++r) {   // r = -1: warm-up
+    if (r == 0) cudaEventRecord(t0, h->stream);
+    if (what == 0) rc = run_residual(h, h->cur, nullptr);
+    else if (what == 1) rc = run_jacobian_blocks(h, h->cur);
+    else { set_error(h, "lcba_time_device: unknown selector"); rc = LCBA_E_ARG; }
+  }
+  cudaEventRecord(t1, h->stream);
+  cudaEventSynchronize(t1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, t0, t1);
+  cudaEventDestroy(t0);
+  cudaEventDestroy(t1);
+  if (rc != LCBA_OK) return rc;
+  *ms_out = (double)ms / reps;
+  return check_launch(h, "lcba_time_device");
+}
+
+// ------------------------------------------------------------------------------ multi-GPU
+extern "C" int lcba_nccl_unique_id(void* id_out128) {
+  if (!id_out128) return LCBA_E_ARG;
+  std::string err;
+  if (!nccl_load(err)) { set_error(nullptr, err); return LCBA_E_NCCL; }
+  ncclUniqueId id;
+  int rc = g_nccl.GetUniqueId(&id);
+  if (rc != 0) { set_error(nullptr, std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(rc)); return LCBA_E_NCCL; }
+  memcpy(id_out128, &id, sizeof(id));
+  return LCBA_OK;
+}
+
+extern "C" int lcba_comm_init(lcba_t* h, int32_t rank, int32_t nranks, const void* id128) {
+  if (!h || !id128 || nranks < 1 || rank < 0 || rank >= nranks) { set_error(h, "lcba_comm_init: bad argument"); return LCBA_E_ARG; }
+  std::string err;
+  if (!nccl_load(err)) { set_error(h, err); return LCBA_E_NCCL; }
+  cudaSetDevice(h->device);
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  int rc = g_nccl.CommInitRank(&h->comm, nranks, id, rank);
+  if (rc != 0) { set_error(h, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(rc)); h->comm = nullptr; return LCBA_E_NCCL; }
+  h->rank = rank;
+  h->nranks = nranks;
+  if (h->have_problem) {
+    // total point count over the ranks (max_nfev = 100 n)
+    double* d = h->d_red;
+    double v = (double)h->P;
+    cudaMemcpyAsync(d, &v, 8, cudaMemcpyHostToDevice, h->stream);
+    LCBA_TRY(allreduce(h, d, 1, NCCL_SUM));
+    cudaMemcpyAsync(&v, d, 8, cudaMemcpyDeviceToHost, h->stream);
+    LCBA_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->P_total = (long long)(v + 0.5);
+  }
+  return LCBA_OK;
+}
+
+// test hook: the 2-D trust-region solver used by the device control kernel
+extern "C" int lcba_debug_tr2d(double B00, double B01, double B11, double g0, double g1, double Delta,
+                               double* p_out, int* newton_out) {
+  if (!p_out) return LCBA_E_ARG;
+  const TR2 t = solve_tr2d(B00, B01, B11, g0, g1, Delta);
+  p_out[0] = t.p0;
+  p_out[1] = t.p1;
+  if (newton_out) *newton_out = t.newton;
+  return LCBA_OK;
+}

@@ -1,0 +1,261 @@
+"""Drop-in ``PySBA`` for the bundle-adjustment step of laserCalib, running on a B200.
+
+Mirrors the surface of the reference ``lasercalib/pySBA.py`` (class ``PySBA``: constructor
+``:28``, ``rotate`` ``:61``, ``project`` ``:76``, ``fun`` ``:92``,
+``bundle_adjustment_sparsity`` ``:103``, ``optimizedParams`` ``:121``, ``bundleAdjust``
+``:132``) with the same names, argument meaning and error behaviour, so that
+``scripts/calibrate_camera.py:62,71`` and ``lasercalib/sba_print.py:13-17`` work unchanged
+after ``from lasercalib_b200.pySBA import PySBA``.
+
+Every numerical method calls the C-ABI of ``liblcba.so`` (include/lcba.h) through ctypes;
+there is no numpy/scipy compute path here and no CPU fallback: without the CUDA library or
+a GPU the calls raise.
+"""
+from __future__ import annotations
+
+import numpy as np
+from scipy.optimize import OptimizeResult
+from scipy.sparse import csr_matrix
+
+from . import _cabi
+
+N_CAM_PARAMS = 11
+
+# scipy/optimize/_lsq/least_squares.py:23-31
+TERMINATION_MESSAGES = {
+    -1: "Improper input parameters status returned from `leastsq`",
+    0: "The maximum number of function evaluations is exceeded.",
+    1: "`gtol` termination condition is satisfied.",
+    2: "`ftol` termination condition is satisfied.",
+    3: "`xtol` termination condition is satisfied.",
+    4: "Both `ftol` and `xtol` termination conditions are satisfied.",
+}
+
+
+class BAResult(OptimizeResult):
+    """OptimizeResult whose large members (``fun``, ``jac``) are produced on first access
+    (the reference materialises a 2N x n CSR Jacobian: ~4 KB per observation)."""
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        object.__setattr__(self, "_lazy", {})
+
+    def set_lazy(self, key, fn):
+        self._lazy[key] = fn
+
+    def __missing__(self, key):
+        lazy = object.__getattribute__(self, "_lazy")
+        if key in lazy:
+            self[key] = lazy.pop(key)()
+            return dict.__getitem__(self, key)
+        raise KeyError(key)
+
+    def __getattr__(self, name):
+        try:
+            return self[name]
+        except KeyError as e:
+            raise AttributeError(name) from e
+
+    def __reduce__(self):
+        for k in list(self._lazy):
+            self[k]
+        return (OptimizeResult, (dict(self),))
+
+
+def _print_header():
+    # scipy/optimize/_lsq/common.py:545-548
+    print("{:^15}{:^15}{:^15}{:^15}{:^15}{:^15}".format(
+        "Iteration", "Total nfev", "Cost", "Cost reduction", "Step norm", "Optimality"))
+
+
+def _print_row(r):
+    # scipy/optimize/_lsq/common.py:551-563
+    cr = " " * 15 if np.isnan(r["cost_reduction"]) else f"{r['cost_reduction']:^15.2e}"
+    sn = " " * 15 if np.isnan(r["step_norm"]) else f"{r['step_norm']:^15.2e}"
+    print(f"{r['iteration']:^15}{r['nfev']:^15}{r['cost']:^15.4e}{cr}{sn}{r['optimality']:^15.2e}")
+
+
+class PySBA:
+    """Python class for Simple Bundle Adjustment (B200 engine behind the reference API)."""
+
+    def __init__(self, cameraArray, points3D, points2D, cameraIndices, point2DIndices,
+                 points3Dfixed=None, pointWeights=None):
+        # attributes and defaults exactly as the reference keeps them (pySBA.py:50-59)
+        self.cameraArray = cameraArray
+        self.points3D = points3D
+        self.points2D = points2D
+        self.cameraIndices = cameraIndices
+        self.point2DIndices = point2DIndices
+        self.points3Dfixed = points3Dfixed
+        if pointWeights is None:
+            pointWeights = np.full_like(point2DIndices, 1)
+        self.pointWeights = pointWeights.reshape((-1, 1))
+        self.points3Dfixed_labeled = None
+        self._engine = None
+        self._problem_key = None
+        self.last_trace = None
+
+    # ---- pickling: device handles never enter the pickle (calibrate_camera.py:86-88) ----
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        d["_engine"] = None
+        d["_problem_key"] = None
+        return d
+
+    def __setstate__(self, d):
+        self.__dict__.update(d)
+
+    # ---- engine plumbing ----
+    def _get_engine(self):
+        if self._engine is None:
+            self._engine = _cabi.Engine()
+        return self._engine
+
+    @staticmethod
+    def _weights_arg(pointWeights):
+        w = np.asarray(pointWeights).reshape(-1)
+        if w.dtype.kind in "iu" and np.all(w == 1):
+            return None, ("ones", w.size)
+        wf = np.ascontiguousarray(w, dtype=np.float64)
+        return wf, ("w", wf.ctypes.data, wf.size, float(wf[:8].sum()))
+
+    def _ensure_problem(self, cams, pts, camera_indices, point_indices, points_2d, pointWeights):
+        """(Re)load the observation set on the device unless it is already resident."""
+        eng = self._get_engine()
+        w, wkey = self._weights_arg(pointWeights)
+        ci = np.asarray(camera_indices)
+        pi = np.asarray(point_indices)
+        p2 = np.asarray(points_2d)
+        key = (cams.shape[0], pts.shape[0], ci.ctypes.data, ci.size, pi.ctypes.data,
+               p2.ctypes.data, wkey)
+        if key != self._problem_key:
+            eng.set_problem(cams, pts, p2, ci, pi, w)
+            self._problem_key = key
+            self._keep = (ci, pi, p2, w)       # keep the keyed buffers alive
+        return eng
+
+    # ---- model (pySBA.py:61-89) ----
+    def rotate(self, points, rot_vecs):
+        """Rotate points by given rotation vectors (Rodrigues), row by row."""
+        return self._get_engine().rotate(np.asarray(points, dtype=np.float64),
+                                         np.asarray(rot_vecs, dtype=np.float64))
+
+    def project(self, points, cameraArray):
+        """Convert 3-D points to 2-D by projecting onto images (per-row camera vector)."""
+        return self._get_engine().project(np.asarray(points, dtype=np.float64),
+                                          np.asarray(cameraArray, dtype=np.float64))
+
+    def fun(self, params, n_cameras, n_points, camera_indices, point_indices, points_2d,
+            pointWeights):
+        """Compute residuals; ``params`` = camera parameters then 3-D coordinates
+        (pySBA.py:92-101).  Interleaved [u0, v0, u1, v1, ...] in the caller's order."""
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        nc = n_cameras * N_CAM_PARAMS
+        cams = params[:nc].reshape((n_cameras, N_CAM_PARAMS))
+        pts = params[nc:].reshape((n_points, 3))
+        eng = self._ensure_problem(cams, pts, camera_indices, point_indices, points_2d,
+                                   pointWeights)
+        r, _ = eng.residuals(params)
+        return r
+
+    def bundle_adjustment_sparsity(self, numCameras, numPoints, cameraIndices, pointIndices):
+        """0/1 pattern (2N, 11C+3P), 28 non-zeros per observation (pySBA.py:103-118);
+        returned as CSR (the reference fills a lil_matrix with the same pattern)."""
+        cameraIndices = np.asarray(cameraIndices)
+        m = cameraIndices.size * 2
+        n = numCameras * N_CAM_PARAMS + numPoints * 3
+        idx = self._get_engine().sparsity_indices(numCameras, numPoints, cameraIndices,
+                                                  pointIndices)
+        indptr = np.arange(0, 14 * (m + 1), 14, dtype=np.int64 if idx.size >= 2**31 else np.int32)
+        return csr_matrix((np.ones(idx.size, dtype=int), idx, indptr), shape=(m, n))
+
+    def optimizedParams(self, params, n_cameras, n_points):
+        """Retrieve camera parameters and 3-D coordinates (views of ``params``)."""
+        nc = n_cameras * N_CAM_PARAMS
+        return params[:nc].reshape((n_cameras, N_CAM_PARAMS)), params[nc:].reshape((n_points, 3))
+
+    # ---- solver (pySBA.py:132-147) ----
+    def bundleAdjust(self, ftol=1e-4, xtol=1e-8, gtol=1e-8, max_nfev=None, verbose=2,
+                     profile=False):
+        """Returns the bundle adjusted parameters (scipy ``OptimizeResult`` layout) and
+        stores them on ``self.cameraArray`` / ``self.points3D``.
+
+        The keyword defaults reproduce the reference call
+        ``least_squares(fun, x0, jac_sparsity=A, verbose=2, x_scale='jac', ftol=ftol,
+        method='trf', jac='3-point')``."""
+        numCameras = self.cameraArray.shape[0]
+        numPoints = self.points3D.shape[0]
+        cams0 = np.ascontiguousarray(self.cameraArray, dtype=np.float64)
+        pts0 = np.ascontiguousarray(self.points3D, dtype=np.float64)
+        eng = self._ensure_problem(cams0, pts0, self.cameraIndices, self.point2DIndices,
+                                   self.points2D, self.pointWeights)
+        eng.set_params(cams0, pts0)
+        try:
+            res, trace = eng.solve(ftol=ftol, xtol=xtol, gtol=gtol, max_nfev=max_nfev or 0,
+                                   verbose=verbose, profile=profile)
+        except _cabi.LcbaError as e:
+            if e.code == -5:
+                raise ValueError("Residuals are not finite in the initial point.") from e
+            raise
+        self.last_trace = trace
+        if verbose == 2:
+            _print_header()
+            for row in trace:
+                _print_row(row)
+        cams, pts = eng.get_params()
+        x = np.hstack((cams.ravel(), pts.ravel()))
+        out = BAResult(x=x, cost=res.cost, optimality=res.optimality,
+                       active_mask=np.zeros_like(x), nfev=int(res.nfev), njev=int(res.njev),
+                       status=int(res.status))
+        out["message"] = TERMINATION_MESSAGES[int(res.status)]
+        out["success"] = int(res.status) > 0
+        out["solve_ms"] = res.solve_ms
+        out["nit"] = int(res.iterations)
+        out.set_lazy("grad", eng.grad)
+        out.set_lazy("fun", lambda: eng.residuals(None)[0])
+        ci, pi = np.asarray(self.cameraIndices), np.asarray(self.point2DIndices)
+
+        def _jac():
+            Jc, Jp = eng.jacobian_blocks(None)
+            A = self.bundle_adjustment_sparsity(numCameras, numPoints, ci, pi)
+            return csr_matrix((np.concatenate([Jc, Jp], axis=2).ravel(), A.indices, A.indptr),
+                              shape=A.shape)
+
+        out.set_lazy("jac", _jac)
+        if verbose >= 1:
+            # scipy/optimize/_lsq/least_squares.py:1038-1043
+            print(out["message"])
+            print("Function evaluations {}, initial cost {:.4e}, final cost {:.4e}, "
+                  "first-order optimality {:.2e}.".format(out["nfev"], res.initial_cost,
+                                                          res.cost, res.optimality))
+        camera_params, points_3d = self.optimizedParams(x, numCameras, numPoints)
+        self.cameraArray = camera_params
+        self.points3D = points_3d
+        return out
+
+    # ---- variants of the reference that are not on the production path ----
+    def _next_row(self, name):
+        raise NotImplementedError(
+            "%s is a 'next' row of the hot-path scope table (SURVEY.md section 8f): not built "
+            "yet; there is deliberately no CPU fallback" % name)
+
+    def bundle_adjustment_camonly(self, ftol=1e-4):
+        self._next_row("bundle_adjustment_camonly")
+
+    def bundleAdjust_nocam(self, ftol=1e-7):
+        self._next_row("bundleAdjust_nocam")
+
+    def bundleAdjust_sharedcam(self, ftol=1e-6):
+        self._next_row("bundleAdjust_sharedcam")
+
+    def bundleAdjust_transform_points_3d(self, ftol=1e-3):
+        self._next_row("bundleAdjust_transform_points_3d")
+
+    def getResiduals(self):
+        """Residuals at the current parameters with unit weights (pySBA.py:207-213; the
+        reference's version raises on a weights broadcast bug — SURVEY App. D)."""
+        numCameras = self.cameraArray.shape[0]
+        numPoints = self.points3D.shape[0]
+        x0 = np.hstack((np.asarray(self.cameraArray).ravel(), np.asarray(self.points3D).ravel()))
+        return self.fun(x0, numCameras, numPoints, self.cameraIndices, self.point2DIndices,
+                        self.points2D, np.full_like(self.point2DIndices, 1))

@@ -1,0 +1,101 @@
+"""CPU-side checks of the C-ABI boundary: the library builds, loads, exports every symbol
+include/lcba.h declares, and fails loudly (no CPU fallback) when there is no GPU."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(REPO, "include", "lcba.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from lasercalib_b200 import build, _cabi
+    build.build()
+    return _cabi.load()
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(lcba_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_are_exported(lib):
+    from lasercalib_b200 import _cabi
+    decl = declared_symbols()
+    assert len(decl) >= 20
+    assert sorted(_cabi.SYMBOLS) == decl
+    out = subprocess.run(["nm", "-D", "--defined-only", _cabi.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (lcba_[a-z0-9_]+)", out))
+    for s in decl:
+        assert s in exported, s
+        assert getattr(lib, s) is not None
+
+
+def test_version_and_default_options(lib):
+    from lasercalib_b200 import _cabi
+    assert lib.lcba_version() == 100
+    o = _cabi.Options()
+    lib.lcba_default_options(ctypes.byref(o))
+    assert (o.ftol, o.xtol, o.gtol, o.max_nfev) == (1e-8, 1e-8, 1e-8, 0)
+
+
+def test_struct_layouts_match_header():
+    from lasercalib_b200 import _cabi
+    assert ctypes.sizeof(_cabi.Options) == 3 * 8 + 8 + 8 * 4
+    assert ctypes.sizeof(_cabi.TraceRow) == 64
+    assert ctypes.sizeof(_cabi.Result) == 3 * 8 + 3 * 8 + 8 + 8 + 7 * 8
+    assert ctypes.sizeof(_cabi.KernelStat) == 48
+
+
+def test_no_cpu_fallback_without_gpu(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from lasercalib_b200 import _cabi
+    with pytest.raises(_cabi.LcbaError, match="no CUDA device"):
+        _cabi.Engine()
+    from lasercalib_b200.pySBA import PySBA
+    sba = PySBA(np.zeros((2, 11)), np.zeros((3, 3)), np.zeros((4, 2)), np.zeros(4, dtype=int),
+                np.zeros(4, dtype=int))
+    with pytest.raises(_cabi.LcbaError):
+        sba.project(np.zeros((1, 3)), np.zeros((1, 11)))
+    with pytest.raises(_cabi.LcbaError):
+        sba.bundleAdjust()
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(REPO, "lasercalib_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(root, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def test_tr2d_solver_matches_scipy(lib):
+    """The device control kernel's 2-D trust-region solver (host-callable hook) against
+    scipy's solve_trust_region_2d (scipy/optimize/_lsq/common.py:171-219)."""
+    from scipy.optimize._lsq.common import solve_trust_region_2d
+    from lasercalib_b200._cabi import debug_tr2d
+    rng = np.random.default_rng(0)
+    for i in range(3000):
+        A = rng.normal(size=(3, 2))
+        if i % 5 == 0:
+            A[:, 1] = A[:, 0] * rng.normal() + 1e-9 * rng.normal(size=3)   # nearly rank-1
+        B = A.T @ A * 10 ** rng.uniform(-3, 3)
+        g = rng.normal(size=2) * 10 ** rng.uniform(-3, 3)
+        D = 10 ** rng.uniform(-3, 3)
+        p, newton = debug_tr2d(B[0, 0], B[0, 1], B[1, 1], g[0], g[1], D)
+        ps, newton_s = solve_trust_region_2d(B, g, D)
+        val = lambda q: 0.5 * q @ B @ q + g @ q
+        assert np.linalg.norm(p) <= D * (1 + 1e-12)
+        # same model value (the quartic route loses digits when B is nearly singular)
+        assert val(p) <= val(ps) + 1e-6 * abs(val(ps)) + 1e-300
+        if newton == newton_s and np.linalg.cond(B) < 1e8:
+            np.testing.assert_allclose(p, ps, rtol=1e-7, atol=1e-9 * D)

@@ -1,0 +1,385 @@
+"""GPU parity tests: the CUDA engine (through the C-ABI / the PySBA drop-in) against the CPU
+oracle and the golden fixtures made from the unmodified reference.  Tolerances follow the
+protocol of SURVEY.md App. C.4 (P1-P5) and are written next to every assertion."""
+import io
+import pickle
+from contextlib import redirect_stdout
+
+import numpy as np
+import pytest
+
+from oracle import pysba_oracle as O
+from lasercalib_b200.synth import make_rig, shuffle_observations
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def PySBA():
+    from lasercalib_b200.pySBA import PySBA as cls
+    return cls
+
+
+@pytest.fixture(scope="module")
+def Engine():
+    from lasercalib_b200._cabi import Engine as cls
+    return cls
+
+
+def _x0(g):
+    return np.hstack((g["cams0"].ravel(), g["pts0"].ravel()))
+
+
+def _sba(PySBA, g, weights=None):
+    return PySBA(g["cams0"].copy(), g["pts0"].copy(), g["points_2d"], g["camera_ind"],
+                 g["point_ind"], pointWeights=weights)
+
+
+# ----------------------------------------------------------------------------- P1 model
+def test_project_rotate_match_reference_outputs(PySBA, golden):
+    g = golden("model_example17")
+    M = int(g["cam_rows_per_point"])
+    rows = np.repeat(g["cams"], M, axis=0)
+    sba = PySBA(g["cams"], g["pts"], np.zeros((1, 2)), np.zeros(1, dtype=int), np.zeros(1, dtype=int))
+    proj = sba.project(g["pts"], rows)
+    # P1: 1e-9 * max(1, |proj|)
+    assert np.all(np.abs(proj - g["proj"]) <= 1e-9 * np.maximum(1.0, np.abs(g["proj"])))
+    np.testing.assert_allclose(sba.rotate(g["pts"], rows[:, :3]), g["rot"], rtol=0, atol=1e-11)
+    r = sba.rotate(g["pts"][:6], g["rv_small"])
+    assert np.all(np.isfinite(r))
+    np.testing.assert_array_equal(r[0], g["pts"][0])            # theta = 0 => identity
+    np.testing.assert_allclose(r, g["rot_small"], rtol=0, atol=1e-11)
+    np.testing.assert_allclose(sba.project(g["pts"][:6], g["cam_small"]), g["proj_small"],
+                               rtol=0, atol=1e-9)
+    # inputs untouched, empty input ok
+    assert sba.project(np.zeros((0, 3)), np.zeros((0, 11))).shape == (0, 2)
+
+
+def test_fun_matches_reference(PySBA, golden):
+    g = golden("model_ring4_planar300")
+    C, P = g["cams0"].shape[0], g["pts0"].shape[0]
+    sba = _sba(PySBA, g)
+    assert sba.pointWeights.dtype == np.int64 and sba.pointWeights.shape == (g["point_ind"].size, 1)
+    f = sba.fun(_x0(g), C, P, g["camera_ind"], g["point_ind"], g["points_2d"], sba.pointWeights)
+    assert f.shape == g["f0"].shape
+    proj_mag = np.maximum(1.0, np.abs(np.repeat(g["proj"], 1, axis=0)).ravel())
+    assert np.all(np.abs(f - g["f0"]) <= 1e-9 * proj_mag)        # P1
+    # float weights
+    sw = _sba(PySBA, g, weights=g["weights"])
+    fw = sw.fun(_x0(g), C, P, g["camera_ind"], g["point_ind"], g["points_2d"], sw.pointWeights)
+    assert np.all(np.abs(fw - g["f0_w"]) <= 2e-9 * proj_mag)
+    # another parameter vector through the same resident problem
+    x1 = _x0(g) * (1 + 1e-4)
+    f1 = sba.fun(x1, C, P, g["camera_ind"], g["point_ind"], g["points_2d"], sba.pointWeights)
+    ref1 = O.fun(x1, C, P, g["camera_ind"], g["point_ind"], g["points_2d"], sba.pointWeights)
+    np.testing.assert_allclose(f1, ref1, rtol=0, atol=1e-8)
+
+
+def test_fun_on_shuffled_observations(PySBA):
+    pb = make_rig("example18", 600, seed=3, variant="volume", p_vis=0.7)
+    sh = shuffle_observations(pb, seed=5)
+    C, P = pb["n_cams"], pb["n_points"]
+    x0 = np.hstack((pb["cams0"].ravel(), pb["pts0"].ravel()))
+    w = O.default_weights(sh["point_ind"])
+    ref = O.fun(x0, C, P, sh["camera_ind"], sh["point_ind"], sh["points_2d"], w)
+    sba = PySBA(pb["cams0"], pb["pts0"], sh["points_2d"], sh["camera_ind"], sh["point_ind"])
+    f = sba.fun(x0, C, P, sh["camera_ind"], sh["point_ind"], sh["points_2d"], sba.pointWeights)
+    np.testing.assert_allclose(f, ref, rtol=0, atol=1e-8)
+
+
+# ----------------------------------------------------------------------------- P2 Jacobian
+def test_jacobian_blocks_vs_truth_and_fd(Engine, golden):
+    g = golden("model_ring4_planar300")
+    eng = Engine()
+    eng.set_problem(g["cams0"], g["pts0"], g["points_2d"], g["camera_ind"], g["point_ind"])
+    Jc, Jp = eng.jacobian_blocks(_x0(g))
+    J = np.concatenate([Jc, Jp], axis=2)
+    Jt = g["J_truth_blocks"]
+    # P2(i): element-wise vs the extended-precision truth of the reference's own fun
+    assert np.abs(J - Jt).max() <= 1e-9 * np.abs(Jt).max()
+    # P2(ii): Frobenius-relative vs scipy's 3-point finite difference
+    Jfd = g["J_fd_blocks"]
+    assert np.linalg.norm(J - Jfd) / np.linalg.norm(Jfd) <= 1e-9
+    # and against the analytic oracle, tightly
+    _, Jc_o, Jp_o = O.jacobian_blocks(g["cams0"], g["pts0"], g["camera_ind"], g["point_ind"],
+                                      O.default_weights(g["point_ind"]))
+    np.testing.assert_allclose(Jc, Jc_o, rtol=0, atol=1e-12 * np.abs(Jt).max())
+    np.testing.assert_allclose(Jp, Jp_o, rtol=0, atol=1e-12 * np.abs(Jt).max())
+    eng.close()
+
+
+def test_jacobian_blocks_weighted_and_shuffled(Engine):
+    pb = shuffle_observations(make_rig("ring8", 500, seed=2, variant="volume", p_vis=0.8), seed=9)
+    rng = np.random.default_rng(1)
+    w = rng.uniform(0.5, 2.0, pb["n_obs"])
+    eng = Engine()
+    eng.set_problem(pb["cams0"], pb["pts0"], pb["points_2d"], pb["camera_ind"], pb["point_ind"], w)
+    Jc, Jp = eng.jacobian_blocks()
+    _, Jc_o, Jp_o = O.jacobian_blocks(pb["cams0"], pb["pts0"], pb["camera_ind"], pb["point_ind"], w)
+    scale = np.abs(Jc_o).max()
+    np.testing.assert_allclose(Jc, Jc_o, rtol=0, atol=1e-12 * scale)
+    np.testing.assert_allclose(Jp, Jp_o, rtol=0, atol=1e-12 * scale)
+    eng.close()
+
+
+# ----------------------------------------------------------------------------- P5 structure
+def test_sparsity_pattern_identical(PySBA, golden):
+    g = golden("model_ring4_planar300")
+    C, P = g["cams0"].shape[0], g["pts0"].shape[0]
+    sba = _sba(PySBA, g)
+    A = sba.bundle_adjustment_sparsity(C, P, g["camera_ind"], g["point_ind"])
+    assert tuple(A.shape) == tuple(g["A_shape"]) and A.nnz == 28 * g["camera_ind"].size
+    assert str(A.dtype) == str(g["A_dtype"])
+    assert np.array_equal(A.indices, g["A_indices"]) and np.array_equal(A.indptr, g["A_indptr"])
+    Ao = O.bundle_adjustment_sparsity(C, P, g["camera_ind"], g["point_ind"])
+    assert (A != Ao).nnz == 0
+
+
+# ------------------------------------------------------------------ reduced camera system
+@pytest.mark.parametrize("rig,npts,pvis,lam", [("ring4", 300, 1.0, 1e-6), ("example18", 400, 0.6, 1e-3),
+                                               ("ring24", 300, 0.5, 1e-8), ("ring64", 200, 0.5, 1e-5)])
+def test_reduced_camera_system_vs_oracle(Engine, rig, npts, pvis, lam):
+    pb = make_rig(rig, npts, seed=1, variant="volume", p_vis=pvis)
+    C, P = pb["n_cams"], pb["n_points"]
+    ci, pi = pb["camera_ind"], pb["point_ind"]
+    w = O.default_weights(pi)
+    x0 = np.hstack((pb["cams0"].ravel(), pb["pts0"].ravel()))
+    f = O.fun(x0, C, P, ci, pi, pb["points_2d"], w)
+    _, Jc, Jp = O.jacobian_blocks(pb["cams0"], pb["pts0"], ci, pi, w)
+    U, gc, V, gp, W = O.normal_blocks(f.reshape(-1, 2), Jc, Jp, C, P, ci, pi)
+    g_or = np.hstack((gc.ravel(), gp.ravel()))
+    sc_or = np.hstack((np.sqrt(np.einsum("caa->ca", U)).ravel(), np.sqrt(np.einsum("paa->pa", V)).ravel()))
+    S_or, rhs_or, _ = O.reduced_camera_system(U, gc, V, gp, W, ci, pi, lam, sc_or)
+    eng = Engine()
+    eng.set_problem(pb["cams0"], pb["pts0"], pb["points_2d"], ci, pi)
+    out = eng.linearize(lam)
+    np.testing.assert_allclose(out["cost"], 0.5 * f @ f, rtol=1e-13)
+    np.testing.assert_allclose(out["grad"], g_or, rtol=0, atol=1e-11 * np.abs(g_or).max())
+    np.testing.assert_allclose(out["scale_inv"], sc_or, rtol=1e-12)
+    assert np.abs(out["S"] - out["S"].T).max() == 0.0
+    assert np.abs(out["S"] - S_or).max() <= 1e-11 * np.abs(S_or).max()
+    assert np.abs(out["rhs"] - rhs_or).max() <= 1e-10 * np.abs(rhs_or).max()
+    eng.close()
+
+
+# ------------------------------------------------------------------------- P3 / P4 solver
+def _run_engine(Engine, g, **kw):
+    eng = Engine()
+    eng.set_problem(g["cams0"], g["pts0"], g["points_2d"], g["camera_ind"], g["point_ind"])
+    res, trace = eng.solve(**kw)
+    cams, pts = eng.get_params()
+    f, cost = eng.residuals()
+    eng.close()
+    return res, trace, cams, pts, f
+
+
+@pytest.mark.parametrize("name", ["ba_ring8_volume1500", "ba_ring4_planar2000", "ba_example18_vis60_800"])
+def test_trajectory_matches_exact_trf_oracle(Engine, golden, name):
+    """Same algorithm on CPU (oracle.trf_exact) and GPU: iteration-by-iteration agreement."""
+    g = golden(name)
+    C = g["cams0"].shape[0]
+    ora = O.trf_exact(g["cams0"], g["pts0"], g["points_2d"], g["camera_ind"], g["point_ind"], ftol=1e-4)
+    res, trace, cams, pts, f = _run_engine(Engine, g, ftol=1e-4)
+    assert res.nfev == ora.nfev and res.njev == ora.njev and res.status == ora.status
+    costs_o = [rec["cost"] for rec in ora.trace] + [ora.cost]
+    costs_g = [row["cost"] for row in trace]
+    assert len(costs_g) == len(costs_o)
+    np.testing.assert_allclose(costs_g, costs_o, rtol=1e-9)
+    regs_o = [rec["reg_term"] for rec in ora.trace]
+    np.testing.assert_allclose([row["reg_term"] for row in trace[1:]], regs_o, rtol=1e-6)
+    np.testing.assert_allclose(res.cost, ora.cost, rtol=1e-10)
+    # final reprojection RMSE within 1e-6 px (north-star tolerance); observed ~1e-10
+    assert abs(O.rmse_px(f) - O.rmse_px(ora.fun)) < 1e-6
+    co = ora.x[: C * 11].reshape(C, 11)
+    rel = np.abs(cams[:, 6:] - co[:, 6:]).max(axis=0) / np.abs(co[:, 6:]).max(axis=0)
+    assert rel.max() < 1e-6, rel                                  # intrinsics, relative
+
+
+def test_first_step_and_final_rmse_vs_tight_scipy(Engine, golden):
+    """P3: one step from the common x0 against scipy with tight LSMR; P4: final RMSE."""
+    g = golden("ba_ring8_volume1500")
+    C, P = g["cams0"].shape[0], g["pts0"].shape[0]
+    res, trace, cams, pts, f = _run_engine(Engine, g, ftol=1e-4, max_nfev=2)
+    t1 = g["tight_x1"]
+    ct = t1[: C * 11].reshape(C, 11)
+    rel = np.abs(cams[:, 6:] - ct[:, 6:]).max(axis=0) / np.abs(ct[:, 6:]).max(axis=0)
+    assert rel.max() < 1e-6, rel                                  # intrinsics <= 1e-6 relative
+    assert np.abs(pts.ravel() - t1[C * 11:]).max() < 1e-4          # points, mm
+    for sl in (slice(0, 3), slice(3, 6)):                          # rotvec / t as blocks
+        assert np.abs(cams[:, sl] - ct[:, sl]).max() / np.abs(ct[:, sl]).max() < 1e-6
+    res, trace, cams, pts, f = _run_engine(Engine, g, ftol=1e-4)
+    assert res.nfev == int(g["tight_nfev"]) and res.status == int(g["tight_status"])
+    w = O.default_weights(g["point_ind"])
+    f_t = O.fun(g["tight_x"], C, P, g["camera_ind"], g["point_ind"], g["points_2d"], w)
+    assert abs(O.rmse_px(f) - O.rmse_px(f_t)) < 1e-6               # north-star RMSE tolerance
+    np.testing.assert_allclose(res.cost, float(g["tight_cost"]), rtol=1e-6)
+    # the reference's default (LSMR atol=btol=1e-6) stops slightly above: report-only bound
+    f_r = O.fun(g["ref_x"], C, P, g["camera_ind"], g["point_ind"], g["points_2d"], w)
+    assert 0 <= O.rmse_px(f_r) - O.rmse_px(f) < 1e-4
+
+
+def test_zero_residual_at_noise_free_ground_truth(Engine):
+    pb = make_rig("ring24", 2000, seed=4, variant="volume", p_vis=0.5, noise_px=0.0)
+    eng = Engine()
+    eng.set_problem(pb["cams_gt"], pb["pts_gt"], pb["points_2d"], pb["camera_ind"], pb["point_ind"])
+    r, cost = eng.residuals()
+    assert np.abs(r).max() < 1e-8
+    res, trace = eng.solve(ftol=1e-8)
+    assert res.status in (1, 2, 3, 4) and res.cost <= cost + 1e-20
+    eng.close()
+
+
+def test_recovers_ground_truth_from_perturbed_start(Engine):
+    pb = make_rig("ring8", 3000, seed=6, variant="volume", noise_px=0.0)
+    eng = Engine()
+    eng.set_problem(pb["cams0"], pb["pts0"], pb["points_2d"], pb["camera_ind"], pb["point_ind"])
+    res, trace = eng.solve(ftol=1e-15, xtol=1e-15, gtol=1e-12, max_nfev=60)
+    r, cost = eng.residuals()
+    assert O.rmse_px(r) < 1e-6                     # noise-free: reprojection error -> 0
+    assert all(b["cost"] <= a["cost"] for a, b in zip(trace, trace[1:]))   # monotone
+    eng.close()
+
+
+# ----------------------------------------------------------------------------- drop-in API
+def test_bundleAdjust_drop_in_surface(PySBA, golden):
+    g = golden("ba_ring4_planar2000")
+    C, P = g["cams0"].shape[0], g["pts0"].shape[0]
+    sba = _sba(PySBA, g)
+    buf = io.StringIO()
+    with redirect_stdout(buf):
+        res = sba.bundleAdjust(1e-4)
+    log = buf.getvalue().splitlines()
+    assert log[0].split() == ["Iteration", "Total", "nfev", "Cost", "Cost", "reduction", "Step",
+                              "norm", "Optimality"]
+    assert log[1].split()[:3] == ["0", "1", "%.4e" % res_initial(g)]
+    assert "termination condition is satisfied" in buf.getvalue()
+    for k in ("x", "cost", "fun", "jac", "grad", "optimality", "active_mask", "nfev", "njev",
+              "status", "message", "success"):
+        assert k in res or hasattr(res, k), k
+    assert res.success and res.status == 2 and res.x.shape == (11 * C + 3 * P,)
+    assert sba.cameraArray.shape == (C, 11) and sba.points3D.shape == (P, 3)
+    assert sba.cameraArray.base is res.x or np.shares_memory(sba.cameraArray, res.x)   # views of res.x
+    assert res.fun.shape == (2 * g["camera_ind"].size,)
+    np.testing.assert_allclose(res.cost, 0.5 * res.fun @ res.fun, rtol=1e-12)
+    J = res.jac
+    assert J.shape == (2 * g["camera_ind"].size, 11 * C + 3 * P) and J.nnz == 28 * g["camera_ind"].size
+    np.testing.assert_allclose(J.T @ res.fun, res.grad, rtol=0, atol=1e-9 * np.abs(res.grad).max())
+    assert abs(res.optimality - np.abs(res.grad).max()) <= 1e-9 * res.optimality
+    # cost no worse than the reference's own run, within 1e-4 relative of it
+    assert res.cost <= float(g["ref_cost"]) * (1 + 1e-9)
+    np.testing.assert_allclose(res.cost, float(g["ref_cost"]), rtol=1e-4)
+    # the object (and the result) must stay picklable (calibrate_camera.py:86-88)
+    sba2 = pickle.loads(pickle.dumps(sba))
+    np.testing.assert_array_equal(sba2.cameraArray, sba.cameraArray)
+    r2 = pickle.loads(pickle.dumps(res))
+    np.testing.assert_array_equal(r2["x"], res.x)
+    # sba_print.py:17 usage
+    r = sba.project(sba.points3D[sba.point2DIndices], sba.cameraArray[sba.cameraIndices]) - sba.points2D
+    np.testing.assert_allclose(r.ravel(), res.fun, atol=1e-8)
+
+
+def res_initial(g):
+    w = O.default_weights(g["point_ind"])
+    f = O.fun(_x0(g), g["cams0"].shape[0], g["pts0"].shape[0], g["camera_ind"], g["point_ind"],
+              g["points_2d"], w)
+    return 0.5 * f @ f
+
+
+def test_weighted_bundle_adjust_vs_oracle(PySBA):
+    pb = make_rig("ring8", 800, seed=8, variant="volume", p_vis=0.8)
+    rng = np.random.default_rng(2)
+    w = rng.uniform(0.5, 2.0, pb["n_obs"])
+    ora = O.trf_exact(pb["cams0"], pb["pts0"], pb["points_2d"], pb["camera_ind"], pb["point_ind"],
+                      weights=w, ftol=1e-4)
+    sba = PySBA(pb["cams0"].copy(), pb["pts0"].copy(), pb["points_2d"], pb["camera_ind"],
+                pb["point_ind"], pointWeights=w)
+    res = sba.bundleAdjust(1e-4, verbose=0)
+    assert res.nfev == ora.nfev and res.status == ora.status
+    np.testing.assert_allclose(res.cost, ora.cost, rtol=1e-9)
+
+
+def test_unsorted_input_gives_same_solution(PySBA):
+    pb = make_rig("example18", 500, seed=3, variant="volume", p_vis=0.7)
+    sh = shuffle_observations(pb, seed=11)
+    a = PySBA(pb["cams0"].copy(), pb["pts0"].copy(), pb["points_2d"], pb["camera_ind"], pb["point_ind"])
+    b = PySBA(pb["cams0"].copy(), pb["pts0"].copy(), sh["points_2d"], sh["camera_ind"], sh["point_ind"])
+    ra, rb = a.bundleAdjust(1e-4, verbose=0), b.bundleAdjust(1e-4, verbose=0)
+    assert ra.nfev == rb.nfev
+    np.testing.assert_allclose(ra.cost, rb.cost, rtol=1e-12)
+    np.testing.assert_allclose(ra.x, rb.x, rtol=1e-9, atol=1e-9)
+    # residual vector comes back in the caller's order
+    perm_cost = 0.5 * rb.fun @ rb.fun
+    np.testing.assert_allclose(perm_cost, rb.cost, rtol=1e-12)
+
+
+# ----------------------------------------------------------------------------- error paths
+def test_error_behaviour(PySBA, Engine):
+    from lasercalib_b200._cabi import LcbaError
+    pb = make_rig("ring4", 50, seed=0)
+    bad = pb["pts0"].copy()
+    bad[0, 0] = np.nan
+    sba = PySBA(pb["cams0"].copy(), bad, pb["points_2d"], pb["camera_ind"], pb["point_ind"])
+    with pytest.raises(ValueError, match="Residuals are not finite in the initial point"):
+        sba.bundleAdjust(1e-4, verbose=0)
+    eng = Engine()
+    ci = pb["camera_ind"].copy()
+    ci[3] = 99
+    with pytest.raises(LcbaError, match="out of range"):
+        eng.set_problem(pb["cams0"], pb["pts0"], pb["points_2d"], ci, pb["point_ind"])
+    ci = pb["camera_ind"].copy()
+    ci[1] = ci[0]
+    with pytest.raises(LcbaError, match="duplicate"):
+        eng.set_problem(pb["cams0"], pb["pts0"], pb["points_2d"], ci, pb["point_ind"])
+    with pytest.raises(LcbaError, match="no problem"):
+        Engine().solve()
+    with pytest.raises(LcbaError, match="64 cameras"):
+        eng.set_problem(np.zeros((65, 11)), pb["pts0"], pb["points_2d"], pb["camera_ind"], pb["point_ind"])
+    with pytest.raises(NotImplementedError):
+        sba.bundleAdjust_nocam()
+    eng.close()
+
+
+def test_point_without_observations_is_left_alone(Engine):
+    pb = make_rig("ring4", 200, seed=0)
+    pts = np.vstack([pb["pts0"], [[1.0, 2.0, 3.0]]])          # extra point nobody sees
+    eng = Engine()
+    eng.set_problem(pb["cams0"], pts, pb["points_2d"], pb["camera_ind"], pb["point_ind"])
+    res, _ = eng.solve(ftol=1e-4)
+    _, out = eng.get_params()
+    np.testing.assert_array_equal(out[-1], [1.0, 2.0, 3.0])
+    assert res.status > 0
+    eng.close()
+
+
+# ------------------------------------------------------------------ full-size properties
+def test_full_size_properties(Engine):
+    """Config-3 scale (24 cameras, 1 M points) through size-independent
+    properties: fun on device == fun via the row-wise project kernel on a sample,
+    J^T f from the linearise pass == directional finite difference of the cost, monotone
+    cost, determinism of the (atomics-free) reductions."""
+    pb = make_rig("ring24", 1_000_000, seed=0, variant="volume", p_vis=0.5)
+    C, P, N = pb["n_cams"], pb["n_points"], pb["n_obs"]
+    assert N > 5_000_000
+    eng = Engine()
+    eng.set_problem(pb["cams0"], pb["pts0"], pb["points_2d"], pb["camera_ind"], pb["point_ind"])
+    r, cost = eng.residuals()
+    np.testing.assert_allclose(0.5 * r @ r, cost, rtol=1e-12)
+    sel = np.random.default_rng(0).choice(N, 5000, replace=False)
+    ref = O.project(pb["pts0"][pb["point_ind"][sel]], pb["cams0"][pb["camera_ind"][sel]]) - pb["points_2d"][sel]
+    np.testing.assert_allclose(r.reshape(-1, 2)[sel], ref, rtol=0, atol=1e-8)
+    lin = eng.linearize(1e-6)
+    g = lin["grad"]
+    x0 = np.hstack((pb["cams0"].ravel(), pb["pts0"].ravel()))
+    v = np.random.default_rng(1).normal(size=x0.size)
+    v[: 11 * C] *= np.maximum(1e-6, np.abs(x0[: 11 * C])) * 1e-3
+    h = 1e-4
+    _, cp = eng.residuals(x0 + h * v, want_r=False)
+    _, cm = eng.residuals(x0 - h * v, want_r=False)
+    np.testing.assert_allclose((cp - cm) / (2 * h), g @ v, rtol=1e-6)
+    lin2 = eng.linearize(1e-6)
+    assert np.array_equal(lin["S"], lin2["S"]) and np.array_equal(lin["grad"], lin2["grad"])   # deterministic
+    res, trace = eng.solve(ftol=1e-4)
+    assert res.status > 0 and all(b["cost"] <= a["cost"] for a, b in zip(trace, trace[1:]))
+    f, c = eng.residuals()
+    assert abs(O.rmse_px(f) - 0.3 * np.sqrt(2)) < 0.02          # sigma = 0.3 px per axis
+    eng.close()
