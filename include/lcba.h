@@ -69,7 +69,8 @@ typedef struct lcba_options {
   int64_t max_nfev;   /* <=0: 100 * (11 C + 3 P) */
   int32_t verbose;    /* 2: keep a per-iteration trace (the host prints scipy's table) */
   int32_t profile;    /* 1: bracket every kernel launch with CUDA events (lcba_get_profile) */
-  int32_t reserved[6];
+  int32_t max_iterations; /* >0: stop after this many outer iterations (bench: time exactly K) */
+  int32_t reserved[5];
 } lcba_options;
 
 /* One row of scipy's verbose=2 table (_lsq/common.py:545-563). */
@@ -94,7 +95,8 @@ typedef struct lcba_result {
   int32_t status;         /* LCBA_STATUS_* */
   int32_t n_trace;        /* rows valid in lcba_get_trace */
   double solve_ms;        /* device time of the whole loop (CUDA events) */
-  double reserved[7];
+  int64_t gpu_launches;   /* kernels launched by this call */
+  double reserved[6];
 } lcba_result;
 
 /* Per-kernel device time (profile=1), accumulated over a solve. */

@@ -25,7 +25,7 @@ SYMBOLS = ["lcba_version", "lcba_create", "lcba_destroy", "lcba_last_error", "lc
 class Options(C.Structure):
     _fields_ = [("ftol", C.c_double), ("xtol", C.c_double), ("gtol", C.c_double),
                 ("max_nfev", C.c_int64), ("verbose", C.c_int32), ("profile", C.c_int32),
-                ("reserved", C.c_int32 * 6)]
+                ("max_iterations", C.c_int32), ("reserved", C.c_int32 * 5)]
 
 
 class TraceRow(C.Structure):
@@ -38,7 +38,7 @@ class Result(C.Structure):
     _fields_ = [("cost", C.c_double), ("optimality", C.c_double), ("initial_cost", C.c_double),
                 ("nfev", C.c_int64), ("njev", C.c_int64), ("iterations", C.c_int64),
                 ("status", C.c_int32), ("n_trace", C.c_int32), ("solve_ms", C.c_double),
-                ("reserved", C.c_double * 7)]
+                ("gpu_launches", C.c_int64), ("reserved", C.c_double * 6)]
 
 
 class KernelStat(C.Structure):
@@ -206,13 +206,15 @@ class Engine:
         return out
 
     # ---- solver ----
-    def solve(self, ftol=1e-8, xtol=1e-8, gtol=1e-8, max_nfev=0, verbose=0, profile=False):
+    def solve(self, ftol=1e-8, xtol=1e-8, gtol=1e-8, max_nfev=0, verbose=0, profile=False,
+              max_iterations=0):
         opt = Options()
         self.lib.lcba_default_options(C.byref(opt))
         opt.ftol, opt.xtol, opt.gtol = ftol, xtol, gtol
         opt.max_nfev = int(max_nfev or 0)
         opt.verbose = int(verbose)
         opt.profile = 1 if profile else 0
+        opt.max_iterations = int(max_iterations or 0)
         res = Result()
         self._check(self.lib.lcba_solve(self.h, C.byref(opt), C.byref(res)))
         rows = (TraceRow * LCBA_MAX_TRACE)()

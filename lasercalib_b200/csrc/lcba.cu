@@ -209,18 +209,23 @@ extern "C" int lcba_create(lcba_t** out, int device) {
   cudaEventCreate(&h->ev0);
   cudaEventCreate(&h->ev1);
   cudaMallocHost((void**)&h->h_ctl, sizeof(Ctl));
-  // opt in to large dynamic shared memory
-  const int big = (int)h->smem_optin;
-  cudaFuncSetAttribute(k_linearize, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-  cudaFuncSetAttribute(k_backsub, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-  cudaFuncSetAttribute(k_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-  cudaFuncSetAttribute(k_residual, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-  cudaFuncSetAttribute(k_jdot, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-  cudaFuncSetAttribute(k_jacobian_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-  if ((e = cudaGetLastError()) != cudaSuccess) {
-    set_error(nullptr, std::string("lcba_create: ") + cudaGetErrorString(e));
-    delete h;
-    return LCBA_E_CUDA;
+  // opt in to large dynamic shared memory (limit = opt-in size minus the kernel's static part)
+  {
+    const void* big_smem_kernels[] = {(const void*)k_linearize, (const void*)k_backsub,
+                                      (const void*)k_schur,     (const void*)k_residual,
+                                      (const void*)k_jdot,      (const void*)k_jacobian_blocks};
+    for (const void* f : big_smem_kernels) {
+      cudaFuncAttributes fa;
+      e = cudaFuncGetAttributes(&fa, f);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(h->smem_optin - fa.sharedSizeBytes));
+      if (e != cudaSuccess) {
+        set_error(nullptr, std::string("lcba_create: shared-memory opt-in: ") + cudaGetErrorString(e));
+        delete h;
+        return LCBA_E_CUDA;
+      }
+    }
   }
   *out = h;
   return LCBA_OK;
@@ -753,6 +758,15 @@ extern "C" int lcba_solve(lcba_t* h, const lcba_options* opt_in, lcba_result* re
   h->trace.clear();
   h->prof.clear();
   h->prof_on = opt.profile != 0;
+  const long long launches0 = h->launches;
+  if (h->comm) {   // total point count over the ranks (max_nfev = 100 n)
+    double v = (double)h->P;
+    LCBA_CUDA(h, cudaMemcpyAsync(h->d_red, &v, 8, cudaMemcpyHostToDevice, h->stream));
+    LCBA_TRY(allreduce(h, h->d_red, 1, NCCL_SUM));
+    LCBA_CUDA(h, cudaMemcpyAsync(&v, h->d_red, 8, cudaMemcpyDeviceToHost, h->stream));
+    LCBA_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->P_total = (long long)(v + 0.5);
+  }
   const long long n_total = (long long)h->C * NCP + 3 * h->P_total;
   const long long max_nfev = opt.max_nfev > 0 ? opt.max_nfev : 100 * n_total;
 
@@ -785,6 +799,7 @@ extern "C" int lcba_solve(lcba_t* h, const lcba_options* opt_in, lcba_result* re
     if (g_norm < opt.gtol) status = LCBA_STATUS_GTOL;
     add_trace(h, iteration, nfev, cost, actual, step_norm, g_norm, h->h_ctl->Delta, last_reg);
     if (status >= 0 || nfev >= max_nfev) break;
+    if (opt.max_iterations > 0 && iteration >= opt.max_iterations) break;
 
     LCBA_TRY(pass_jdot(h));
     LCBA_TRY(pass_schur(h, nullptr));
@@ -857,6 +872,7 @@ extern "C" int lcba_solve(lcba_t* h, const lcba_options* opt_in, lcba_result* re
   res->status = status;
   res->n_trace = (int)h->trace.size();
   res->solve_ms = ms;
+  res->gpu_launches = h->launches - launches0;
   h->prof_on = false;
   return LCBA_OK;
 }
@@ -983,16 +999,6 @@ extern "C" int lcba_comm_init(lcba_t* h, int32_t rank, int32_t nranks, const voi
   if (rc != 0) { set_error(h, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(rc)); h->comm = nullptr; return LCBA_E_NCCL; }
   h->rank = rank;
   h->nranks = nranks;
-  if (h->have_problem) {
-    // total point count over the ranks (max_nfev = 100 n)
-    double* d = h->d_red;
-    double v = (double)h->P;
-    cudaMemcpyAsync(d, &v, 8, cudaMemcpyHostToDevice, h->stream);
-    LCBA_TRY(allreduce(h, d, 1, NCCL_SUM));
-    cudaMemcpyAsync(&v, d, 8, cudaMemcpyDeviceToHost, h->stream);
-    LCBA_CUDA(h, cudaStreamSynchronize(h->stream));
-    h->P_total = (long long)(v + 0.5);
-  }
   return LCBA_OK;
 }
 

@@ -21,7 +21,7 @@
 
 namespace lcba {
 
-constexpr int SCHUR_MAX_HW = 28;     // half-warps (duo blocks) per CTA
+constexpr int SCHUR_MAX_HW = 24;     // half-warps (duo blocks) per CTA
 constexpr int YS_LD = 80;            // doubles per (point, slot): 5 K-slices x 4 row groups x 4
 
 struct SchurHw {          // one duo block = 2x2 camera pairs
@@ -122,7 +122,7 @@ __device__ __forceinline__ void outer9(double (&acc)[9], const double (&a)[3], c
       acc[3 * i + j] = SUB ? fma(-a[i], b[j], acc[3 * i + j]) : fma(a[i], b[j], acc[3 * i + j]);
 }
 
-__global__ void __maxnreg__(144)
+__global__ void __maxnreg__(168)
 k_schur(const double* __restrict__ tab, const double* __restrict__ pts,
         const double* __restrict__ wgt, const uint32_t* __restrict__ obs_start,
         const unsigned long long* __restrict__ mask, const double* __restrict__ Lz, long long P,
