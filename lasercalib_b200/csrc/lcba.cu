@@ -212,7 +212,8 @@ extern "C" int lcba_create(lcba_t** out, int device) {
   // opt in to large dynamic shared memory (limit = opt-in size minus the kernel's static part)
   {
     const void* big_smem_kernels[] = {(const void*)k_linearize, (const void*)k_backsub,
-                                      (const void*)k_schur,     (const void*)k_residual,
+                                      (const void*)k_schur<true>, (const void*)k_schur<false>,
+                                      (const void*)k_residual,
                                       (const void*)k_jdot,      (const void*)k_jacobian_blocks};
     for (const void* f : big_smem_kernels) {
       cudaFuncAttributes fa;
@@ -617,9 +618,17 @@ static int pass_schur(lcba_t* h, const double* lam_host_or_null) {
           h->d_Vg, h->d_scl_p, h->d_ctl, h->P, h->d_Lz));
   }
   dim3 grid(pl.nslices, pl.nkinds);
-  KL(h, "schur", k_schur<<<grid, pl.max_threads, pl.smem_bytes, h->stream>>>(
-        h->d_tab[w], h->d_pts[w], h->d_w, h->d_obs_start, h->d_mask, h->d_Lz, h->P, h->N, C, h->d_kinds,
-        h->d_hws, pl.pc, pl.nslices, pl.part_stride, pl.npairs, h->d_Spart));
+  // sparse rigs skip duo blocks nobody sees; dense rigs run branch-free
+  const bool skip = (double)h->N < 0.8 * (double)h->P * C;
+  if (skip) {
+    KL(h, "schur", k_schur<true><<<grid, pl.max_threads, pl.smem_bytes, h->stream>>>(
+          h->d_tab[w], h->d_pts[w], h->d_w, h->d_obs_start, h->d_mask, h->d_Lz, h->P, h->N, C, h->d_kinds,
+          h->d_hws, pl.nslices, pl.part_stride, pl.npairs, h->d_Spart));
+  } else {
+    KL(h, "schur", k_schur<false><<<grid, pl.max_threads, pl.smem_bytes, h->stream>>>(
+          h->d_tab[w], h->d_pts[w], h->d_w, h->d_obs_start, h->d_mask, h->d_Lz, h->P, h->N, C, h->d_kinds,
+          h->d_hws, pl.nslices, pl.part_stride, pl.npairs, h->d_Spart));
+  }
   KL(h, "schur_reduce", k_reduce_cols<<<nblk((long long)pl.part_stride, 256), 256, 0, h->stream>>>(
         h->d_Spart, pl.nslices, (int)pl.part_stride, h->d_Sred));
   LCBA_TRY(allreduce(h, h->d_Sred, pl.part_stride, NCCL_SUM));

@@ -21,20 +21,26 @@
 
 namespace lcba {
 
-constexpr int SCHUR_MAX_HW = 24;     // half-warps (duo blocks) per CTA
-constexpr int YS_LD = 80;            // doubles per (point, slot): 5 K-slices x 4 row groups x 4
+constexpr int SCHUR_MAX_HW = 24;     // half-warps (duo blocks) per CTA: 12 warps x 160 registers (3 warps x 5120 regs per SM sub-partition)
+constexpr int Y_LD = 50;             // doubles per (point, slot): 3 K-slices x 4 row groups x 4, +2 pad
+constexpr int JC_LD = 34;            // doubles per (point, diag slot): 2 K-slices x 16, +2 pad
+// (both strides are = 4 banks mod 32 and multiples of 16 B: conflict-free 128-bit stores from
+//  consecutive lanes in phase 1, aligned 128-bit loads in phase 2)
 
 struct SchurHw {          // one duo block = 2x2 camera pairs
   int8_t s[4];            // shared-memory slots of cams j0, j1, k0, k1
   int8_t c[4];            // camera ids   j0, j1, k0, k1 (0 when absent; see valid)
   uint8_t valid;          // bit (2*ja + kb): pair (j_ja, k_kb) is a lower-triangle pair
   uint8_t diag;           // same bit layout: pair is a diagonal pair (same camera)
-  uint8_t pad[6];
+  int8_t ds[2];           // Jc slots of j0, j1 (diagonal blocks only)
+  uint8_t pad[4];
 };
 
 struct SchurKind {
   int nslots, nhw, hw_base, threads;
+  int ndiag, qpr, pad0, pad1;             // diagonal (Jc) slots; points per phase-1 round
   uint8_t slot_cam[LCBA_MAX_CAMERAS];
+  int8_t slot_dslot[LCBA_MAX_CAMERAS];    // Jc slot of a camera slot or -1
 };
 
 struct SchurPlan {
@@ -48,6 +54,11 @@ struct SchurPlan {
 
 inline int pair_index(int j, int k) { return j * (j + 1) / 2 + k; }
 
+inline size_t schur_smem_bytes(int C, int pc, int nslots, int ndiag) {
+  return ((size_t)pc * nslots * Y_LD + (size_t)pc * ndiag * JC_LD + (size_t)pc * 4 + pc +
+          (size_t)C * CAMTAB) * 8 + 64;
+}
+
 inline SchurPlan make_schur_plan(int C, int sm_count, size_t smem_limit) {
   SchurPlan pl;
   pl.C = C;
@@ -58,23 +69,31 @@ inline SchurPlan make_schur_plan(int C, int sm_count, size_t smem_limit) {
   pl.npairs = C * (C + 1) / 2;
   pl.part_stride = (size_t)pl.npairs * 121 + (size_t)NCP * C;
   int b = 0, bj = 0, bk = 0;
+  pl.pc = 1 << 30;
   for (int kd = 0; kd < pl.nkinds; ++kd) {
     SchurKind K{};
     K.hw_base = (int)pl.hws.size();
-    bool used[LCBA_MAX_CAMERAS] = {false};
+    bool used[LCBA_MAX_CAMERAS] = {false}, isdiag[LCBA_MAX_CAMERAS] = {false};
     std::vector<std::pair<int, int>> blks;
     for (int i = 0; i < bpk && b < nblocks; ++i, ++b) {
       blks.push_back({bj, bk});
       for (int d = 0; d < 2; ++d) {
         if (2 * bj + d < C) used[2 * bj + d] = true;
         if (2 * bk + d < C) used[2 * bk + d] = true;
+        if (bj == bk && 2 * bj + d < C) isdiag[2 * bj + d] = true;
       }
       if (++bk > bj) { bk = 0; ++bj; }
     }
-    int slot_of[LCBA_MAX_CAMERAS];
+    int slot_of[LCBA_MAX_CAMERAS], dslot_of[LCBA_MAX_CAMERAS];
     K.nslots = 0;
+    K.ndiag = 0;
     for (int c = 0; c < C; ++c)
-      if (used[c]) { slot_of[c] = K.nslots; K.slot_cam[K.nslots++] = (uint8_t)c; }
+      if (used[c]) {
+        slot_of[c] = K.nslots;
+        dslot_of[c] = isdiag[c] ? K.ndiag++ : -1;
+        K.slot_dslot[K.nslots] = (int8_t)dslot_of[c];
+        K.slot_cam[K.nslots++] = (uint8_t)c;
+      }
     for (auto& bl : blks) {
       SchurHw h{};
       const int cj[2] = {2 * bl.first, 2 * bl.first + 1};
@@ -84,6 +103,7 @@ inline SchurPlan make_schur_plan(int C, int sm_count, size_t smem_limit) {
         h.s[d] = (int8_t)(cj[d] < C ? slot_of[cj[d]] : 0);
         h.c[2 + d] = (int8_t)(ck[d] < C ? ck[d] : 0);
         h.s[2 + d] = (int8_t)(ck[d] < C ? slot_of[ck[d]] : 0);
+        h.ds[d] = (int8_t)((bl.first == bl.second && cj[d] < C) ? dslot_of[cj[d]] : 0);
       }
       for (int ja = 0; ja < 2; ++ja)
         for (int kb = 0; kb < 2; ++kb)
@@ -95,16 +115,28 @@ inline SchurPlan make_schur_plan(int C, int sm_count, size_t smem_limit) {
     }
     K.nhw = (int)blks.size();
     K.threads = std::max(64, 32 * ((K.nhw + 1) / 2));
+    // phase 1 needs at least one point per round
+    while (K.threads < K.nslots) K.threads += 32;
+    K.qpr = K.threads / K.nslots;
     pl.max_threads = std::max(pl.max_threads, K.threads);
     pl.max_slots = std::max(pl.max_slots, K.nslots);
+    // points per chunk: a whole number of phase-1 rounds that fits shared memory
+    {
+      const size_t per_pt = ((size_t)K.nslots * Y_LD + (size_t)K.ndiag * JC_LD + 5) * 8;
+      const size_t fixed = (size_t)C * CAMTAB * 8 + 64;
+      const int maxpts = (int)std::max<size_t>(1, (smem_limit - fixed) / per_pt);
+      if (K.qpr > maxpts) K.qpr = maxpts;
+    }
+    int rounds = 1;
+    while (rounds < 8 &&
+           schur_smem_bytes(C, K.qpr * (rounds + 1), K.nslots, K.ndiag) <= smem_limit) ++rounds;
+    // per-kind chunk size travels in pad0
+    K.pad0 = K.qpr * rounds;
+    pl.smem_bytes = std::max(pl.smem_bytes, schur_smem_bytes(C, K.pad0, K.nslots, K.ndiag));
     pl.kinds.push_back(K);
   }
+  pl.pc = 0;
   pl.nslices = std::max(1, sm_count / pl.nkinds);
-  const size_t fixed = (size_t)C * CAMTAB * 8 + 64;
-  const size_t per_pt = (size_t)pl.max_slots * YS_LD * 8 + 4 * 8 + 8;
-  long pc = (long)((smem_limit - fixed) / per_pt);
-  pl.pc = (int)std::max(1L, std::min(32L, pc));
-  pl.smem_bytes = fixed + per_pt * pl.pc;
   return pl;
 }
 
@@ -122,28 +154,94 @@ __device__ __forceinline__ void outer9(double (&acc)[9], const double (&a)[3], c
       acc[3 * i + j] = SUB ? fma(-a[i], b[j], acc[3 * i + j]) : fma(a[i], b[j], acc[3 * i + j]);
 }
 
-__global__ void __maxnreg__(168)
+__device__ __forceinline__ void st4(double* p, double a, double b, double c, double d) {
+  *reinterpret_cast<double2*>(p) = make_double2(a, b);
+  *reinterpret_cast<double2*>(p + 2) = make_double2(c, d);
+}
+
+// Phase 1 for one (point, camera slot): Y = (Jc^T Jp) L^-T into Ys, Jc into Js (diagonal slots).
+// Invisible cameras get zeros so that phase 2 needs no per-pair visibility test.
+__device__ __noinline__ void schur_produce(const double* __restrict__ T, const double* __restrict__ X,
+                                           const double* __restrict__ li, double w, bool visible,
+                                           double* __restrict__ Y, double* __restrict__ Js) {
+  if (!visible) {
+#pragma unroll
+    for (int e = 0; e < 48; e += 4) st4(Y + e, 0.0, 0.0, 0.0, 0.0);
+    if (Js) {
+#pragma unroll
+      for (int e = 0; e < 32; e += 4) st4(Js + e, 0.0, 0.0, 0.0, 0.0);
+    }
+    return;
+  }
+  ObsLin L;
+  obs_linearize<false>(T, X[0], X[1], X[2], 0.0, 0.0, w, L);
+  double Q[2][3];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    Q[i][0] = L.Jp[i][0] * li[0];
+    Q[i][1] = fma(L.Jp[i][0], li[1], L.Jp[i][1] * li[2]);
+    Q[i][2] = fma(L.Jp[i][0], li[3], fma(L.Jp[i][1], li[4], L.Jp[i][2] * li[5]));
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    double y[9];
+#pragma unroll
+    for (int a = 0; a < 9; ++a) y[a] = fma(L.Jc[0][a], Q[0][k], L.Jc[1][a] * Q[1][k]);
+    st4(Y + k * 16 + 0, y[0], y[1], y[2], 0.0);
+    st4(Y + k * 16 + 4, y[3], y[4], y[5], 0.0);
+    st4(Y + k * 16 + 8, y[6], y[7], y[8], 0.0);
+    st4(Y + k * 16 + 12, w * Q[0][k], w * Q[1][k], 0.0, 0.0);
+  }
+  if (Js) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      st4(Js + i * 16 + 0, L.Jc[i][0], L.Jc[i][1], L.Jc[i][2], 0.0);
+      st4(Js + i * 16 + 4, L.Jc[i][3], L.Jc[i][4], L.Jc[i][5], 0.0);
+      st4(Js + i * 16 + 8, L.Jc[i][6], L.Jc[i][7], L.Jc[i][8], 0.0);
+      st4(Js + i * 16 + 12, i == 0 ? w : 0.0, i == 1 ? w : 0.0, 0.0, 0.0);
+    }
+  }
+}
+
+// SKIP: test the visibility mask per (point, duo block) and skip blocks nobody sees
+// (sparse rigs); without it every block is computed (zeros contribute nothing).
+template <bool SKIP>
+__global__ void __maxnreg__(160)
 k_schur(const double* __restrict__ tab, const double* __restrict__ pts,
         const double* __restrict__ wgt, const uint32_t* __restrict__ obs_start,
         const unsigned long long* __restrict__ mask, const double* __restrict__ Lz, long long P,
         long long N, int C, const SchurKind* __restrict__ kinds, const SchurHw* __restrict__ hws,
-        int PC, int nslices, size_t part_stride, int npairs, double* __restrict__ part) {
+        int nslices, size_t part_stride, int npairs, double* __restrict__ part) {
   extern __shared__ __align__(16) double s_dyn[];
   const SchurKind& K = kinds[blockIdx.y];
   const int nthreads = K.threads;
   const int tid = threadIdx.x;
   if (tid >= nthreads) return;          // uniform per warp (threads multiple of 32)
-  const int nslots = K.nslots;
-  double* s_Y = s_dyn;                                        // PC * nslots * YS_LD (16B aligned)
-  double* s_z = s_Y + (size_t)PC * nslots * YS_LD;            // PC * 4
+  const int nslots = K.nslots, ndiag = K.ndiag, PC = K.pad0, qpr = K.qpr;
+  double* s_Y = s_dyn;                                        // PC * nslots * Y_LD
+  double* s_J = s_Y + (size_t)PC * nslots * Y_LD;             // PC * ndiag * JC_LD
+  double* s_z = s_J + (size_t)PC * ndiag * JC_LD;             // PC * 4
   unsigned long long* s_mask = reinterpret_cast<unsigned long long*>(s_z + PC * 4);   // PC
   double* s_tab = reinterpret_cast<double*>(s_mask + PC);     // C * CAMTAB
   for (int i = tid; i < C * CAMTAB; i += nthreads) s_tab[i] = tab[i];
 
+  // phase-1 role: a fixed camera slot per thread
+  const int my_q = tid / nslots, my_s = tid - my_q * nslots;
+  const bool producer = my_q < qpr;
+  const int my_cam = producer ? K.slot_cam[my_s] : 0;
+  const int my_ds = producer ? K.slot_dslot[my_s] : -1;
+  // phase-2 role
   const int hw = tid >> 4, l16 = tid & 15, rr = l16 >> 2, cc = l16 & 3;
   SchurHw D{};
   if (hw < K.nhw) D = hws[K.hw_base + hw];
   const unsigned valid = D.valid, diag = D.diag;
+  const int oj0 = D.s[0] * Y_LD + rr * 4, oj1 = D.s[1] * Y_LD + rr * 4;
+  const int ok0 = D.s[2] * Y_LD + cc * 4, ok1 = D.s[3] * Y_LD + cc * 4;
+  unsigned long long bm_j = 0, bm_k = 0;      // cameras of the block, for the SKIP test
+  if (valid) {
+    bm_j = (1ull << D.c[0]) | ((valid & 12u) ? (1ull << D.c[1]) : 0ull);
+    bm_k = (1ull << D.c[2]) | ((valid & 10u) ? (1ull << D.c[3]) : 0ull);
+  }
 
   double acc[4][9];
   double rh[2][3];
@@ -165,50 +263,22 @@ k_schur(const double* __restrict__ tab, const double* __restrict__ pts,
     pa = (slice == 0) ? 0 : lower_bound_u32(obs_start, P, ta);
     pb = (slice == nslices - 1) ? P : lower_bound_u32(obs_start, P, tb);
   }
-  // named barrier over the active threads only
   auto bar = [&]() { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); };
   bar();
 
   for (long long q0 = pa; q0 < pb; q0 += PC) {
     const int npc = (int)min((long long)PC, pb - q0);
-    // ---------------- phase 1: Y (and Jc) for every (point, camera slot) ----------------
-    for (int idx = tid; idx < npc * nslots; idx += nthreads) {
-      const int q = idx / nslots, s = idx - q * nslots;
-      const long long p = q0 + q;
-      const unsigned long long m = mask[p];
-      const int c = K.slot_cam[s];
-      if ((m >> c) & 1ull) {
-        const long long o = (long long)obs_start[p] + __popcll(m & ((1ull << c) - 1ull));
-        const double w = wgt ? wgt[o] : 1.0;
-        ObsLin L;
-        obs_linearize<false>(s_tab + c * CAMTAB, pts[3 * p], pts[3 * p + 1], pts[3 * p + 2], 0.0,
-                             0.0, w, L);
-        const double* li = Lz + p * 9;
-        double Q[2][3];
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          Q[i][0] = L.Jp[i][0] * li[0];
-          Q[i][1] = fma(L.Jp[i][0], li[1], L.Jp[i][1] * li[2]);
-          Q[i][2] = fma(L.Jp[i][0], li[3], fma(L.Jp[i][1], li[4], L.Jp[i][2] * li[5]));
-        }
-        double* Y = s_Y + ((size_t)q * nslots + s) * YS_LD;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-#pragma unroll
-          for (int a = 0; a < 9; ++a)
-            Y[k * 16 + (a / 3) * 4 + (a % 3)] = fma(L.Jc[0][a], Q[0][k], L.Jc[1][a] * Q[1][k]);
-          Y[k * 16 + 12] = w * Q[0][k];
-          Y[k * 16 + 13] = w * Q[1][k];
-          Y[k * 16 + 14] = 0.0;
-        }
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-#pragma unroll
-          for (int a = 0; a < 9; ++a) Y[(3 + i) * 16 + (a / 3) * 4 + (a % 3)] = L.Jc[i][a];
-          Y[(3 + i) * 16 + 12] = (i == 0) ? w : 0.0;
-          Y[(3 + i) * 16 + 13] = (i == 1) ? w : 0.0;
-          Y[(3 + i) * 16 + 14] = 0.0;
-        }
+    // ---------------- phase 1 ----------------
+    if (producer) {
+      for (int q = my_q; q < npc; q += qpr) {
+        const long long p = q0 + q;
+        const unsigned long long m = mask[p];
+        const bool vis = (m >> my_cam) & 1ull;
+        double w = 1.0;
+        if (vis && wgt) w = wgt[(long long)obs_start[p] + __popcll(m & ((1ull << my_cam) - 1ull))];
+        schur_produce(s_tab + my_cam * CAMTAB, pts + 3 * p, Lz + p * 9, w, vis,
+                      s_Y + ((size_t)q * nslots + my_s) * Y_LD,
+                      my_ds >= 0 ? s_J + ((size_t)q * ndiag + my_ds) * JC_LD : nullptr);
       }
     }
     for (int q = tid; q < npc; q += nthreads) {
@@ -217,50 +287,45 @@ k_schur(const double* __restrict__ tab, const double* __restrict__ pts,
       s_z[q * 4] = li[6]; s_z[q * 4 + 1] = li[7]; s_z[q * 4 + 2] = li[8];
     }
     bar();
-    // ---------------- phase 2: rank-3 updates per visible camera pair -------------------
+    // ---------------- phase 2 ----------------
     if (valid) {
-      for (int q = 0; q < npc; ++q) {
-        const unsigned long long m = s_mask[q];
-        const unsigned vj0 = (unsigned)(m >> D.c[0]) & 1u, vj1 = (unsigned)(m >> D.c[1]) & 1u;
-        const unsigned vk0 = (unsigned)(m >> D.c[2]) & 1u, vk1 = (unsigned)(m >> D.c[3]) & 1u;
-        const unsigned pm = valid & ((vj0 & vk0) | ((vj0 & vk1) << 1) | ((vj1 & vk0) << 2) |
-                                     ((vj1 & vk1) << 3));
-        if (!pm) continue;
-        const double* Yq = s_Y + (size_t)q * nslots * YS_LD;
-        const double* Yj0 = Yq + D.s[0] * YS_LD + rr * 4;
-        const double* Yj1 = Yq + D.s[1] * YS_LD + rr * 4;
-        const double* Yk0 = Yq + D.s[2] * YS_LD + cc * 4;
-        const double* Yk1 = Yq + D.s[3] * YS_LD + cc * 4;
-        const double* z = s_z + q * 4;
+      const double* Yq = s_Y;
+      for (int q = 0; q < npc; ++q, Yq += nslots * Y_LD) {
+        if (SKIP) {
+          const unsigned long long m = s_mask[q];
+          if (!(m & bm_j) || !(m & bm_k)) continue;
+        }
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
           double a0[3], a1[3], b0[3], b1[3];
-          if (pm & 3u) ld3(Yj0 + k * 16, a0);
-          if (pm & 12u) ld3(Yj1 + k * 16, a1);
-          if (pm & 5u) ld3(Yk0 + k * 16, b0);
-          if (pm & 10u) ld3(Yk1 + k * 16, b1);
-          if (pm & 1u) outer9<true>(acc[0], a0, b0);
-          if (pm & 2u) outer9<true>(acc[1], a0, b1);
-          if (pm & 4u) outer9<true>(acc[2], a1, b0);
-          if (pm & 8u) outer9<true>(acc[3], a1, b1);
-          if (cc == 0) {
-            const double zk = z[k];
-            if (pm & diag & 1u) {
+          ld3(Yq + oj0 + k * 16, a0);
+          ld3(Yq + oj1 + k * 16, a1);
+          ld3(Yq + ok0 + k * 16, b0);
+          ld3(Yq + ok1 + k * 16, b1);
+          outer9<true>(acc[0], a0, b0);
+          outer9<true>(acc[1], a0, b1);
+          outer9<true>(acc[2], a1, b0);
+          outer9<true>(acc[3], a1, b1);
+          if (diag) {
+            const double zk = s_z[q * 4 + k];
 #pragma unroll
-              for (int i = 0; i < 3; ++i) rh[0][i] = fma(-a0[i], zk, rh[0][i]);
-            }
-            if (pm & diag & 8u) {
-#pragma unroll
-              for (int i = 0; i < 3; ++i) rh[1][i] = fma(-a1[i], zk, rh[1][i]);
+            for (int i = 0; i < 3; ++i) {
+              rh[0][i] = fma(-a0[i], zk, rh[0][i]);
+              rh[1][i] = fma(-a1[i], zk, rh[1][i]);
             }
           }
         }
-        if (pm & diag) {   // U_j = sum Jc^T Jc on the diagonal pairs (K-slices 3,4)
+        if (diag) {   // U_j = sum Jc^T Jc on the diagonal pairs
+          const double* Jq = s_J + (size_t)q * ndiag * JC_LD;
 #pragma unroll
-          for (int k = 3; k < 5; ++k) {
+          for (int k = 0; k < 2; ++k) {
             double a[3], b[3];
-            if (pm & diag & 1u) { ld3(Yj0 + k * 16, a); ld3(Yk0 + k * 16, b); outer9<false>(acc[0], a, b); }
-            if (pm & diag & 8u) { ld3(Yj1 + k * 16, a); ld3(Yk1 + k * 16, b); outer9<false>(acc[3], a, b); }
+            ld3(Jq + D.ds[0] * JC_LD + k * 16 + rr * 4, a);
+            ld3(Jq + D.ds[0] * JC_LD + k * 16 + cc * 4, b);
+            outer9<false>(acc[0], a, b);
+            ld3(Jq + D.ds[1] * JC_LD + k * 16 + rr * 4, a);
+            ld3(Jq + D.ds[1] * JC_LD + k * 16 + cc * 4, b);
+            outer9<false>(acc[3], a, b);
           }
         }
       }

@@ -385,5 +385,6 @@ def test_full_size_properties(Engine):
     res, trace = eng.solve(ftol=1e-4)
     assert res.status > 0 and all(b["cost"] <= a["cost"] for a, b in zip(trace, trace[1:]))
     f, c = eng.residuals()
-    assert abs(O.rmse_px(f) - 0.3 * np.sqrt(2)) < 0.02          # sigma = 0.3 px per axis
+    # sigma = 0.3 px per axis; ~12 views fit 3 point parameters => rmse ~ 0.424*sqrt(1-3/24)
+    assert 0.37 < O.rmse_px(f) < 0.43
     eng.close()
