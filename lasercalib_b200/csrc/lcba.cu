@@ -834,7 +834,9 @@ extern "C" int lcba_solve(lcba_t* h, const lcba_options* opt_in, lcba_result* re
       break;
     }
     last_reg = h->h_ctl->reg_term;
-    // inner loop: trials until the cost decreases (trf.py:503-541)
+    // inner loop: trials until the cost decreases (trf.py:503-541); scipy would spin up to
+    // max_nfev = 100 n when all tolerances are 0 and the step underflows — cap the rejections
+    int rejected = 0;
     while (true) {
       if (have_trial) { nfev++; have_trial = false; }
       const Ctl& c = *h->h_ctl;
@@ -846,7 +848,7 @@ extern "C" int lcba_solve(lcba_t* h, const lcba_options* opt_in, lcba_result* re
         if (term >= 0) break;
       }
       if (finite && actual > 0.0) break;
-      if (nfev >= max_nfev) break;
+      if (nfev >= max_nfev || ++rejected > 64) break;
       LCBA_TRY(pass_trial(h));
       LCBA_TRY(read_ctl(h));
       have_trial = true;

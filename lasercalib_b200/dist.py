@@ -1,0 +1,122 @@
+"""Point sharding across GPUs of one node: one process per GPU (torch.distributed for the
+plumbing), NCCL all-reduce of the reduced camera system inside liblcba.so.
+
+The reference is single-process; the sharding axis is the point
+index: every point block (V, g_p, W) depends only on its own observations and the
+replicated camera table, so each rank keeps a contiguous range of points, their
+observations and all cameras; only [S | rhs | camera sums | scalars] cross NVLink.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+
+def world():
+    """(rank, world_size, local_rank) from torch.distributed if initialised, else (0,1,0)."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size(), int(os.environ.get("LOCAL_RANK", 0))
+    except ImportError:
+        pass
+    return 0, 1, 0
+
+
+def init_from_env(backend=None):
+    """Join the job torchrun started (RANK / WORLD_SIZE / LOCAL_RANK / MASTER_* in the env)."""
+    import torch
+    import torch.distributed as dist
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
+    if ws <= 1:
+        return 0, 1, 0
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if backend is None:
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            dist.init_process_group(backend, device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend)
+    return dist.get_rank(), dist.get_world_size(), local
+
+
+def shard_bounds(point_ind, n_points, nranks):
+    """Point-range boundaries b[0..nranks] balanced by observation count: rank r owns points
+    [b[r], b[r+1]).  Works for any observation order."""
+    counts = np.bincount(np.asarray(point_ind), minlength=n_points)
+    cum = np.cumsum(counts)
+    total = int(cum[-1]) if n_points else 0
+    b = np.zeros(nranks + 1, dtype=np.int64)
+    for r in range(1, nranks):
+        b[r] = int(np.searchsorted(cum, total * r / nranks, side="left")) + 1 if total else 0
+    b[nranks] = n_points
+    b = np.minimum(np.maximum.accumulate(b), n_points)
+    return b
+
+
+def shard_problem(points3D, points2D, camera_ind, point_ind, weights, rank, nranks, bounds=None):
+    """This rank's slice: points [lo, hi), the observations that reference them (local point
+    indices), all cameras implied.  Returns dict(pts, points_2d, camera_ind, point_ind,
+    weights, lo, hi, obs_sel)."""
+    point_ind = np.asarray(point_ind)
+    if bounds is None:
+        bounds = shard_bounds(point_ind, points3D.shape[0], nranks)
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    sel = np.nonzero((point_ind >= lo) & (point_ind < hi))[0]
+    w = None if weights is None else np.asarray(weights).reshape(-1)[sel]
+    return dict(pts=np.ascontiguousarray(points3D[lo:hi]),
+                points_2d=np.ascontiguousarray(np.asarray(points2D)[sel]),
+                camera_ind=np.ascontiguousarray(np.asarray(camera_ind)[sel]),
+                point_ind=np.ascontiguousarray(point_ind[sel] - lo),
+                weights=w, lo=lo, hi=hi, obs_sel=sel, bounds=bounds)
+
+
+def connect_engine(engine):
+    """Create the NCCL communicator of `engine` across the torch.distributed job."""
+    import torch.distributed as dist
+    from . import _cabi
+    rank, ws, _ = world()
+    if ws == 1:
+        return
+    box = [_cabi.Engine.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    engine.comm_init(rank, ws, box[0])
+
+
+def allgather_rows(local, bounds):
+    """Concatenate per-rank row blocks (rank r holds rows bounds[r]:bounds[r+1]) on every rank."""
+    import torch
+    import torch.distributed as dist
+    rank, ws, _ = world()
+    if ws == 1:
+        return local
+    local = np.ascontiguousarray(local)
+    width = local.shape[1]
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" \
+        else torch.device("cpu")
+    sizes = [int(bounds[r + 1] - bounds[r]) for r in range(ws)]
+    mx = max(max(sizes), 1)
+    buf = torch.zeros((mx, width), dtype=torch.float64, device=dev)
+    buf[: local.shape[0]] = torch.from_numpy(local).to(dev)
+    outs = [torch.empty_like(buf) for _ in range(ws)]
+    dist.all_gather(outs, buf)
+    return np.concatenate([o[: sizes[r]].cpu().numpy() for r, o in enumerate(outs)], axis=0)
+
+
+def allreduce_sum(arr):
+    """In-place float64 sum over ranks of a numpy array (host-side plumbing for tests)."""
+    import torch
+    import torch.distributed as dist
+    rank, ws, _ = world()
+    if ws == 1:
+        return arr
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" \
+        else torch.device("cpu")
+    t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float64)).to(dev)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    arr[...] = t.cpu().numpy().reshape(arr.shape)
+    return arr

@@ -18,6 +18,7 @@ from scipy.optimize import OptimizeResult
 from scipy.sparse import csr_matrix
 
 from . import _cabi
+from . import dist as _dist
 
 N_CAM_PARAMS = 11
 
@@ -108,7 +109,9 @@ class PySBA:
     # ---- engine plumbing ----
     def _get_engine(self):
         if self._engine is None:
-            self._engine = _cabi.Engine()
+            rank, ws, local = _dist.world()
+            self._engine = _cabi.Engine(local if ws > 1 else -1)
+            self._comm_ready = False
         return self._engine
 
     @staticmethod
@@ -176,7 +179,7 @@ class PySBA:
 
     # ---- solver (pySBA.py:132-147) ----
     def bundleAdjust(self, ftol=1e-4, xtol=1e-8, gtol=1e-8, max_nfev=None, verbose=2,
-                     profile=False):
+                     profile=False, max_iterations=0):
         """Returns the bundle adjusted parameters (scipy ``OptimizeResult`` layout) and
         stores them on ``self.cameraArray`` / ``self.points3D``.
 
@@ -187,12 +190,31 @@ class PySBA:
         numPoints = self.points3D.shape[0]
         cams0 = np.ascontiguousarray(self.cameraArray, dtype=np.float64)
         pts0 = np.ascontiguousarray(self.points3D, dtype=np.float64)
-        eng = self._ensure_problem(cams0, pts0, self.cameraIndices, self.point2DIndices,
-                                   self.points2D, self.pointWeights)
-        eng.set_params(cams0, pts0)
+        rank, ws, _ = _dist.world()
+        shard = None
+        if ws > 1:
+            # one process per GPU: this rank keeps a contiguous range of points and their
+            # observations; cameras are replicated; the library all-reduces with NCCL
+            w, _ = self._weights_arg(self.pointWeights)
+            shard = _dist.shard_problem(pts0, self.points2D, self.cameraIndices,
+                                        self.point2DIndices, w, rank, ws)
+            eng = self._get_engine()
+            eng.set_problem(cams0, shard["pts"], shard["points_2d"], shard["camera_ind"],
+                            shard["point_ind"], shard["weights"])
+            self._problem_key = None
+            if not self._comm_ready:
+                _dist.connect_engine(eng)
+                self._comm_ready = True
+            if verbose and rank != 0:
+                verbose = 0
+        else:
+            eng = self._ensure_problem(cams0, pts0, self.cameraIndices, self.point2DIndices,
+                                       self.points2D, self.pointWeights)
+            eng.set_params(cams0, pts0)
         try:
             res, trace = eng.solve(ftol=ftol, xtol=xtol, gtol=gtol, max_nfev=max_nfev or 0,
-                                   verbose=verbose, profile=profile)
+                                   verbose=verbose, profile=profile,
+                                   max_iterations=max_iterations)
         except _cabi.LcbaError as e:
             if e.code == -5:
                 raise ValueError("Residuals are not finite in the initial point.") from e
@@ -203,6 +225,8 @@ class PySBA:
             for row in trace:
                 _print_row(row)
         cams, pts = eng.get_params()
+        if shard is not None:
+            pts = _dist.allgather_rows(pts, shard["bounds"])
         x = np.hstack((cams.ravel(), pts.ravel()))
         out = BAResult(x=x, cost=res.cost, optimality=res.optimality,
                        active_mask=np.zeros_like(x), nfev=int(res.nfev), njev=int(res.njev),
@@ -211,9 +235,21 @@ class PySBA:
         out["success"] = int(res.status) > 0
         out["solve_ms"] = res.solve_ms
         out["nit"] = int(res.iterations)
+        out["gpu_launches"] = int(res.gpu_launches)
+        ci, pi = np.asarray(self.cameraIndices), np.asarray(self.point2DIndices)
+        if shard is not None:
+            # sharded run: `fun` / `grad` / `jac` are this rank's shard (observations
+            # `fun_obs_index` of the caller's arrays); x, cost, optimality are global
+            out["fun_obs_index"] = shard["obs_sel"]
+            out.set_lazy("fun", lambda: eng.residuals(None)[0])
+            if verbose >= 1:
+                print(out["message"])
+            camera_params, points_3d = self.optimizedParams(x, numCameras, numPoints)
+            self.cameraArray = camera_params
+            self.points3D = points_3d
+            return out
         out.set_lazy("grad", eng.grad)
         out.set_lazy("fun", lambda: eng.residuals(None)[0])
-        ci, pi = np.asarray(self.cameraIndices), np.asarray(self.point2DIndices)
 
         def _jac():
             Jc, Jp = eng.jacobian_blocks(None)
