@@ -16,28 +16,38 @@ namespace lcba {
 constexpr int LIN_THREADS = 256;
 constexpr int LIN_WARPS = LIN_THREADS / 32;
 constexpr int CAMSUM = 22;          // per camera: g_c (11) then diag(J^T J) (11)
-constexpr int STAGE_LD = 23;        // odd stride for the per-warp staging tile
+constexpr int CTAB_LD = 23;         // odd row stride of the warp-private camera tables
 
 struct BinRange { long long p0, p1; long long o0; int nobs; };
 
-// Bin b owns the points whose first observation index lies in [b*B, (b+1)*B).
-__device__ __forceinline__ void bin_range(const uint32_t* __restrict__ obs_start, long long P,
-                                          long long bin, int B, BinRange* s_bin) {
+// Bin b owns the points whose first observation index lies in [b*B, (b+1)*B); the first
+// point of every bin is precomputed once at ingest (k_bin_table), so a CTA finds its work
+// with two dependent loads instead of two binary searches.
+__global__ void k_bin_table(const uint32_t* __restrict__ obs_start, long long P, long long nbins,
+                            int B, int32_t* __restrict__ bin_p0) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > nbins) return;
+  bin_p0[b] = (b == nbins) ? (int32_t)P
+                           : (int32_t)lower_bound_u32(obs_start, P, (unsigned long long)b * B);
+}
+
+__device__ __forceinline__ void bin_range(const uint32_t* __restrict__ obs_start,
+                                          const int32_t* __restrict__ bin_p0, long long bin,
+                                          BinRange* s_bin) {
   if (threadIdx.x == 0) {
-    const long long p0 = lower_bound_u32(obs_start, P, (unsigned long long)bin * B);
-    const long long p1 = lower_bound_u32(obs_start, P, (unsigned long long)(bin + 1) * B);
+    const long long p0 = bin_p0[bin], p1 = bin_p0[bin + 1];
+    const uint32_t a = obs_start[p0], b = obs_start[p1];
     s_bin->p0 = p0;
     s_bin->p1 = p1;
-    s_bin->o0 = obs_start[p0];
-    s_bin->nobs = (int)(obs_start[p1] - obs_start[p0]);
+    s_bin->o0 = a;
+    s_bin->nobs = (int)(b - a);
   }
   __syncthreads();
 }
 
-// dynamic smem layout (doubles): tab[C*CAMTAB | even] pv[256*9] stage[8*32*23] ctab[8*C*22]
+// dynamic smem layout (doubles): tab[C*CAMTAB | even] pv[256*9] ctab[8*C*23]
 __host__ __device__ inline size_t linearize_smem_doubles(int C) {
-  return (size_t)((C * CAMTAB + 1) & ~1) + LIN_THREADS * 9 + LIN_WARPS * 32 * STAGE_LD +
-         (size_t)LIN_WARPS * C * CAMSUM;
+  return (size_t)((C * CAMTAB + 1) & ~1) + LIN_THREADS * 9 + (size_t)LIN_WARPS * C * CTAB_LD;
 }
 
 // Vg[p][0..5] = V (00,01,02,11,12,22), Vg[p][6..8] = g_p.
@@ -46,31 +56,29 @@ __global__ void __launch_bounds__(LIN_THREADS)
 k_linearize(const double* __restrict__ tab, const double* __restrict__ pts,
             const double2* __restrict__ uv, const uint8_t* __restrict__ cam,
             const int32_t* __restrict__ pt, const double* __restrict__ wgt,
-            const uint32_t* __restrict__ obs_start, long long P, long long nbins, int B, int C,
-            double* __restrict__ Vg, double* __restrict__ cam_part,
+            const uint32_t* __restrict__ obs_start, const int32_t* __restrict__ bin_p0,
+            long long nbins, int C, double* __restrict__ Vg, double* __restrict__ cam_part,
             double* __restrict__ cost_part) {
   extern __shared__ double s_dyn[];
   double* s_tab = s_dyn;
   double* s_pv = s_dyn + ((C * CAMTAB + 1) & ~1);
-  double* s_stage = s_pv + LIN_THREADS * 9;
-  double* s_ctab = s_stage + LIN_WARPS * 32 * STAGE_LD;
+  double* s_ctab = s_pv + LIN_THREADS * 9;
   __shared__ double s_red[32];
   __shared__ BinRange s_bin;
-  __shared__ uint8_t s_cam[LIN_THREADS];
 
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
   load_tables_smem(tab, s_tab, C);
-  for (int i = t; i < LIN_WARPS * C * CAMSUM; i += LIN_THREADS) s_ctab[i] = 0.0;
+  for (int i = t; i < LIN_WARPS * C * CTAB_LD; i += LIN_THREADS) s_ctab[i] = 0.0;
   double cost = 0.0;
-  double* my_ctab = s_ctab + (size_t)wid * C * CAMSUM;
-  double* my_stage = s_stage + (size_t)wid * 32 * STAGE_LD;
+  double* my_ctab = s_ctab + (size_t)wid * C * CTAB_LD;
 
   for (long long bin = blockIdx.x; bin < nbins; bin += gridDim.x) {
-    bin_range(obs_start, P, bin, B, &s_bin);     // contains __syncthreads (also orders smem reuse)
+    bin_range(obs_start, bin_p0, bin, &s_bin);   // contains __syncthreads (also orders smem reuse)
     const long long p0 = s_bin.p0, o0 = s_bin.o0;
     const long long npts = s_bin.p1 - p0;
     const int nobs = s_bin.nobs;
     uint8_t c8 = 255;
+    double cv[CAMSUM];
     if (t < nobs) {
       const long long o = o0 + t;
       c8 = cam[o];
@@ -91,18 +99,31 @@ k_linearize(const double* __restrict__ tab, const double* __restrict__ pts,
       pv[6] = fma(L.Jp[0][0], L.ru, L.Jp[1][0] * L.rv);
       pv[7] = fma(L.Jp[0][1], L.ru, L.Jp[1][1] * L.rv);
       pv[8] = fma(L.Jp[0][2], L.ru, L.Jp[1][2] * L.rv);
-      double* sg = my_stage + lane * STAGE_LD;
 #pragma unroll
       for (int a = 0; a < 9; ++a) {
-        sg[a] = fma(L.Jc[0][a], L.ru, L.Jc[1][a] * L.rv);
-        sg[11 + a] = fma(L.Jc[0][a], L.Jc[0][a], L.Jc[1][a] * L.Jc[1][a]);
+        cv[a] = fma(L.Jc[0][a], L.ru, L.Jc[1][a] * L.rv);
+        cv[11 + a] = fma(L.Jc[0][a], L.Jc[0][a], L.Jc[1][a] * L.Jc[1][a]);
       }
-      sg[9] = w * L.ru;
-      sg[10] = w * L.rv;
-      sg[20] = w * w;
-      sg[21] = w * w;
+      cv[9] = w * L.ru;
+      cv[10] = w * L.rv;
+      cv[20] = w * w;
+      cv[21] = w * w;
     }
-    s_cam[t] = c8;
+    // per-camera sums into the warp-private table: lanes that share a camera take turns
+    // (rank among their peers), all other lanes update their own row concurrently
+    {
+      const unsigned peers = __match_any_sync(0xffffffffu, (int)c8);
+      const int rank = (c8 == 255) ? -1 : __popc(peers & ((1u << lane) - 1u));
+      const int maxrank = __reduce_max_sync(0xffffffffu, rank);
+      for (int r = 0; r <= maxrank; ++r) {
+        if (rank == r) {
+          double* row = my_ctab + c8 * CTAB_LD;
+#pragma unroll
+          for (int v = 0; v < CAMSUM; ++v) row[v] += cv[v];
+        }
+        __syncwarp();
+      }
+    }
     __syncthreads();
     // per-point sums (fixed order => deterministic)
     for (long long idx = t; idx < npts * 9; idx += LIN_THREADS) {
@@ -113,13 +134,6 @@ k_linearize(const double* __restrict__ tab, const double* __restrict__ pts,
       for (int i = f0; i < f1; ++i) s += s_pv[i * 9 + e];
       Vg[(p0 + q) * 9 + e] = s;
     }
-    // per-camera sums: lane v owns value v of the warp-private table
-    if (lane < CAMSUM) {
-      for (int i = 0; i < 32; ++i) {
-        const int c = s_cam[wid * 32 + i];
-        if (c != 255) my_ctab[c * CAMSUM + lane] += my_stage[i * STAGE_LD + lane];
-      }
-    }
     __syncthreads();
   }
   // flush
@@ -128,7 +142,8 @@ k_linearize(const double* __restrict__ tab, const double* __restrict__ pts,
   for (int i = t; i < C * CAMSUM; i += LIN_THREADS) {
     double s = 0.0;
 #pragma unroll
-    for (int w = 0; w < LIN_WARPS; ++w) s += s_ctab[(size_t)w * C * CAMSUM + i];
+    for (int w = 0; w < LIN_WARPS; ++w)
+      s += s_ctab[(size_t)w * C * CTAB_LD + (i / CAMSUM) * CTAB_LD + (i % CAMSUM)];
     out[i] = s;
   }
   const double cs = block_sum(cost, s_red);
@@ -278,8 +293,9 @@ constexpr int BS_K = 9;
 __global__ void __launch_bounds__(LIN_THREADS)
 k_backsub(const double* __restrict__ tab, const double* __restrict__ pts,
           const uint8_t* __restrict__ cam, const int32_t* __restrict__ pt,
-          const double* __restrict__ wgt, const uint32_t* __restrict__ obs_start, long long P,
-          long long nbins, int B, int C, const double* __restrict__ Vg,
+          const double* __restrict__ wgt, const uint32_t* __restrict__ obs_start,
+          const int32_t* __restrict__ bin_p0, long long nbins, int C,
+          const double* __restrict__ Vg,
           const double* __restrict__ Lz, const double* __restrict__ scl,
           const double* __restrict__ gt_c, const double* __restrict__ gt_p,
           const double* __restrict__ pc /* 11C GN step, cameras */, double* __restrict__ gn_p,
@@ -300,7 +316,7 @@ k_backsub(const double* __restrict__ tab, const double* __restrict__ pts,
   for (int k = 0; k < BS_K; ++k) acc[k] = 0.0;
 
   for (long long bin = blockIdx.x; bin < nbins; bin += gridDim.x) {
-    bin_range(obs_start, P, bin, B, &s_bin);
+    bin_range(obs_start, bin_p0, bin, &s_bin);
     const long long p0 = s_bin.p0, o0 = s_bin.o0;
     const long long npts = s_bin.p1 - p0;
     const int nobs = s_bin.nobs;

@@ -21,7 +21,10 @@
 
 namespace lcba {
 
-constexpr int SCHUR_MAX_HW = 24;     // half-warps (duo blocks) per CTA: 12 warps x 160 registers (3 warps x 5120 regs per SM sub-partition)
+constexpr int SCHUR_MAX_HW = 20;     // consumer half-warps (duo blocks) per CTA: 10 consumer + 2 producer
+                                     // warps x 160 registers (3 warps x 5120 regs per SM sub-partition)
+constexpr int SCHUR_PROD_WARPS = 2;
+constexpr int SCHUR_STAGES = 2;
 constexpr int Y_LD = 50;             // doubles per (point, slot): 3 K-slices x 4 row groups x 4, +2 pad
 constexpr int JC_LD = 34;            // doubles per (point, diag slot): 2 K-slices x 16, +2 pad
 // (both strides are = 4 banks mod 32 and multiples of 16 B: conflict-free 128-bit stores from
@@ -38,7 +41,7 @@ struct SchurHw {          // one duo block = 2x2 camera pairs
 
 struct SchurKind {
   int nslots, nhw, hw_base, threads;
-  int ndiag, qpr, pad0, pad1;             // diagonal (Jc) slots; points per phase-1 round
+  int ndiag, qpr, pad0, pad1;             // diagonal (Jc) slots; first producer thread; points per stage
   uint8_t slot_cam[LCBA_MAX_CAMERAS];
   int8_t slot_dslot[LCBA_MAX_CAMERAS];    // Jc slot of a camera slot or -1
 };
@@ -55,7 +58,7 @@ struct SchurPlan {
 inline int pair_index(int j, int k) { return j * (j + 1) / 2 + k; }
 
 inline size_t schur_smem_bytes(int C, int pc, int nslots, int ndiag) {
-  return ((size_t)pc * nslots * Y_LD + (size_t)pc * ndiag * JC_LD + (size_t)pc * 4 + pc +
+  return ((size_t)pc * nslots * Y_LD + (size_t)pc * ndiag * JC_LD + (size_t)pc * 6 +
           (size_t)C * CAMTAB) * 8 + 64;
 }
 
@@ -114,25 +117,20 @@ inline SchurPlan make_schur_plan(int C, int sm_count, size_t smem_limit) {
       pl.hws.push_back(h);
     }
     K.nhw = (int)blks.size();
-    K.threads = std::max(64, 32 * ((K.nhw + 1) / 2));
-    // phase 1 needs at least one point per round
-    while (K.threads < K.nslots) K.threads += 32;
-    K.qpr = K.threads / K.nslots;
+    const int cons_threads = 32 * ((K.nhw + 1) / 2);
+    K.threads = cons_threads + 32 * SCHUR_PROD_WARPS;
+    K.qpr = cons_threads;                       // first producer thread
     pl.max_threads = std::max(pl.max_threads, K.threads);
     pl.max_slots = std::max(pl.max_slots, K.nslots);
-    // points per chunk: a whole number of phase-1 rounds that fits shared memory
+    // points per stage: SCHUR_STAGES stages must fit shared memory
     {
-      const size_t per_pt = ((size_t)K.nslots * Y_LD + (size_t)K.ndiag * JC_LD + 5) * 8;
+      const size_t per_pt = ((size_t)K.nslots * Y_LD + (size_t)K.ndiag * JC_LD + 6) * 8;
       const size_t fixed = (size_t)C * CAMTAB * 8 + 64;
-      const int maxpts = (int)std::max<size_t>(1, (smem_limit - fixed) / per_pt);
-      if (K.qpr > maxpts) K.qpr = maxpts;
+      const int sp = (int)((smem_limit - fixed) / (per_pt * SCHUR_STAGES));
+      K.pad0 = std::max(1, std::min(16, sp));
     }
-    int rounds = 1;
-    while (rounds < 8 &&
-           schur_smem_bytes(C, K.qpr * (rounds + 1), K.nslots, K.ndiag) <= smem_limit) ++rounds;
-    // per-kind chunk size travels in pad0
-    K.pad0 = K.qpr * rounds;
-    pl.smem_bytes = std::max(pl.smem_bytes, schur_smem_bytes(C, K.pad0, K.nslots, K.ndiag));
+    pl.smem_bytes = std::max(pl.smem_bytes,
+                             schur_smem_bytes(C, K.pad0 * SCHUR_STAGES, K.nslots, K.ndiag));
     pl.kinds.push_back(K);
   }
   pl.pc = 0;
@@ -205,6 +203,18 @@ __device__ __noinline__ void schur_produce(const double* __restrict__ T, const d
 
 // SKIP: test the visibility mask per (point, duo block) and skip blocks nobody sees
 // (sparse rigs); without it every block is computed (zeros contribute nothing).
+//
+// Warp-specialised: the last SCHUR_PROD_WARPS warps are producers (phase 1: latency-bound
+// Jacobian + Y into a 2-stage shared-memory ring), the others consumers (phase 2: the DFMA
+// stream).  Stages are handed over with named barriers: producers bar.arrive FULL[s] /
+// bar.sync EMPTY[s], consumers bar.sync FULL[s] / bar.arrive EMPTY[s].
+__device__ __forceinline__ void nbar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void nbar_arrive(int id, int count) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
 template <bool SKIP>
 __global__ void __maxnreg__(160)
 k_schur(const double* __restrict__ tab, const double* __restrict__ pts,
@@ -217,20 +227,63 @@ k_schur(const double* __restrict__ tab, const double* __restrict__ pts,
   const int nthreads = K.threads;
   const int tid = threadIdx.x;
   if (tid >= nthreads) return;          // uniform per warp (threads multiple of 32)
-  const int nslots = K.nslots, ndiag = K.ndiag, PC = K.pad0, qpr = K.qpr;
-  double* s_Y = s_dyn;                                        // PC * nslots * Y_LD
-  double* s_J = s_Y + (size_t)PC * nslots * Y_LD;             // PC * ndiag * JC_LD
-  double* s_z = s_J + (size_t)PC * ndiag * JC_LD;             // PC * 4
-  unsigned long long* s_mask = reinterpret_cast<unsigned long long*>(s_z + PC * 4);   // PC
-  double* s_tab = reinterpret_cast<double*>(s_mask + PC);     // C * CAMTAB
-  for (int i = tid; i < C * CAMTAB; i += nthreads) s_tab[i] = tab[i];
+  const int nslots = K.nslots, ndiag = K.ndiag, SP = K.pad0, prod0 = K.qpr;
+  // per stage: Y[SP][nslots][Y_LD] J[SP][ndiag][JC_LD] z[SP][4] mask[SP] pad[SP] (even => 16 B)
+  const size_t stage_doubles = (size_t)SP * nslots * Y_LD + (size_t)SP * ndiag * JC_LD + SP * 6;
+  double* s_tab = s_dyn + SCHUR_STAGES * stage_doubles;      // C * CAMTAB
+  enum { BAR_FULL = 2, BAR_EMPTY = 4, BAR_PROD = 6 };
 
-  // phase-1 role: a fixed camera slot per thread
-  const int my_q = tid / nslots, my_s = tid - my_q * nslots;
-  const bool producer = my_q < qpr;
-  const int my_cam = producer ? K.slot_cam[my_s] : 0;
-  const int my_ds = producer ? K.slot_dslot[my_s] : -1;
-  // phase-2 role
+  // slice boundaries balanced by observation count
+  const int slice = blockIdx.x;
+  long long pa, pb;
+  {
+    const unsigned long long ta = (unsigned long long)N * slice / nslices;
+    const unsigned long long tb = (unsigned long long)N * (slice + 1) / nslices;
+    pa = (slice == 0) ? 0 : lower_bound_u32(obs_start, P, ta);
+    pb = (slice == nslices - 1) ? P : lower_bound_u32(obs_start, P, tb);
+  }
+  const long long nchunks = (pb - pa + SP - 1) / SP;
+
+  if (tid >= prod0) {
+    // =============================== producers ===============================
+    const int ptid = tid - prod0, nprod = nthreads - prod0;
+    for (int i = ptid; i < C * CAMTAB; i += nprod) s_tab[i] = tab[i];
+    nbar_sync(BAR_PROD, nprod);
+    for (long long c = 0; c < nchunks + SCHUR_STAGES; ++c) {
+      const int st = (int)(c % SCHUR_STAGES);
+      if (c >= SCHUR_STAGES) nbar_sync(BAR_EMPTY + st, nthreads);
+      if (c >= nchunks) continue;
+      double* s_Y = s_dyn + st * stage_doubles;
+      double* s_J = s_Y + (size_t)SP * nslots * Y_LD;
+      double* s_z = s_J + (size_t)SP * ndiag * JC_LD;
+      unsigned long long* s_mask = reinterpret_cast<unsigned long long*>(s_z + SP * 4);
+      const long long q0 = pa + c * SP;
+      const int npc = (int)min((long long)SP, pb - q0);
+      for (int idx = ptid; idx < npc * nslots; idx += nprod) {
+        const int q = idx / nslots, sl = idx - q * nslots;
+        const long long p = q0 + q;
+        const unsigned long long m = mask[p];
+        const int cam = K.slot_cam[sl];
+        const int ds = K.slot_dslot[sl];
+        const bool vis = (m >> cam) & 1ull;
+        double w = 1.0;
+        if (vis && wgt) w = wgt[(long long)obs_start[p] + __popcll(m & ((1ull << cam) - 1ull))];
+        schur_produce(s_tab + cam * CAMTAB, pts + 3 * p, Lz + p * 9, w, vis,
+                      s_Y + ((size_t)q * nslots + sl) * Y_LD,
+                      ds >= 0 ? s_J + ((size_t)q * ndiag + ds) * JC_LD : nullptr);
+      }
+      for (int q = ptid; q < npc; q += nprod) {
+        s_mask[q] = mask[q0 + q];
+        const double* li = Lz + (q0 + q) * 9;
+        s_z[q * 4] = li[6]; s_z[q * 4 + 1] = li[7]; s_z[q * 4 + 2] = li[8];
+      }
+      __threadfence_block();
+      nbar_arrive(BAR_FULL + st, nthreads);
+    }
+    return;
+  }
+
+  // =============================== consumers ===============================
   const int hw = tid >> 4, l16 = tid & 15, rr = l16 >> 2, cc = l16 & 3;
   SchurHw D{};
   if (hw < K.nhw) D = hws[K.hw_base + hw];
@@ -242,7 +295,6 @@ k_schur(const double* __restrict__ tab, const double* __restrict__ pts,
     bm_j = (1ull << D.c[0]) | ((valid & 12u) ? (1ull << D.c[1]) : 0ull);
     bm_k = (1ull << D.c[2]) | ((valid & 10u) ? (1ull << D.c[3]) : 0ull);
   }
-
   double acc[4][9];
   double rh[2][3];
 #pragma unroll
@@ -254,40 +306,14 @@ k_schur(const double* __restrict__ tab, const double* __restrict__ pts,
 #pragma unroll
     for (int j = 0; j < 3; ++j) rh[i][j] = 0.0;
 
-  // slice boundaries balanced by observation count
-  const int slice = blockIdx.x;
-  long long pa, pb;
-  {
-    const unsigned long long ta = (unsigned long long)N * slice / nslices;
-    const unsigned long long tb = (unsigned long long)N * (slice + 1) / nslices;
-    pa = (slice == 0) ? 0 : lower_bound_u32(obs_start, P, ta);
-    pb = (slice == nslices - 1) ? P : lower_bound_u32(obs_start, P, tb);
-  }
-  auto bar = [&]() { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); };
-  bar();
-
-  for (long long q0 = pa; q0 < pb; q0 += PC) {
-    const int npc = (int)min((long long)PC, pb - q0);
-    // ---------------- phase 1 ----------------
-    if (producer) {
-      for (int q = my_q; q < npc; q += qpr) {
-        const long long p = q0 + q;
-        const unsigned long long m = mask[p];
-        const bool vis = (m >> my_cam) & 1ull;
-        double w = 1.0;
-        if (vis && wgt) w = wgt[(long long)obs_start[p] + __popcll(m & ((1ull << my_cam) - 1ull))];
-        schur_produce(s_tab + my_cam * CAMTAB, pts + 3 * p, Lz + p * 9, w, vis,
-                      s_Y + ((size_t)q * nslots + my_s) * Y_LD,
-                      my_ds >= 0 ? s_J + ((size_t)q * ndiag + my_ds) * JC_LD : nullptr);
-      }
-    }
-    for (int q = tid; q < npc; q += nthreads) {
-      s_mask[q] = mask[q0 + q];
-      const double* li = Lz + (q0 + q) * 9;
-      s_z[q * 4] = li[6]; s_z[q * 4 + 1] = li[7]; s_z[q * 4 + 2] = li[8];
-    }
-    bar();
-    // ---------------- phase 2 ----------------
+  for (long long c = 0; c < nchunks; ++c) {
+    const int st = (int)(c % SCHUR_STAGES);
+    const double* s_Y = s_dyn + st * stage_doubles;
+    const double* s_J = s_Y + (size_t)SP * nslots * Y_LD;
+    const double* s_z = s_J + (size_t)SP * ndiag * JC_LD;
+    const unsigned long long* s_mask = reinterpret_cast<const unsigned long long*>(s_z + SP * 4);
+    const int npc = (int)min((long long)SP, pb - (pa + c * SP));
+    nbar_sync(BAR_FULL + st, nthreads);
     if (valid) {
       const double* Yq = s_Y;
       for (int q = 0; q < npc; ++q, Yq += nslots * Y_LD) {
@@ -330,7 +356,7 @@ k_schur(const double* __restrict__ tab, const double* __restrict__ pts,
         }
       }
     }
-    bar();
+    nbar_arrive(BAR_EMPTY + st, nthreads);
   }
   // ---------------- write the slice partial (every lower-triangle entry exactly once) ----
   if (valid) {
