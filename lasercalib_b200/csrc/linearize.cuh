@@ -290,7 +290,7 @@ k_point_factor(const double* __restrict__ Vg, const double* __restrict__ scl, do
 // part[block][0..8]: (Jg~.Jg~, Jg~.Jp, Jp.Jp) , scaled-space (a.a, a.b, b.b) with a = g_h,
 // b = gn_h (points part), unscaled (g~.g~, g~.p, p.p) (points part)
 constexpr int BS_K = 9;
-__global__ void __launch_bounds__(LIN_THREADS)
+__global__ void __launch_bounds__(LIN_THREADS, 3)
 k_backsub(const double* __restrict__ tab, const double* __restrict__ pts,
           const uint8_t* __restrict__ cam, const int32_t* __restrict__ pt,
           const double* __restrict__ wgt, const uint32_t* __restrict__ obs_start,
@@ -320,7 +320,7 @@ k_backsub(const double* __restrict__ tab, const double* __restrict__ pts,
     const long long p0 = s_bin.p0, o0 = s_bin.o0;
     const long long npts = s_bin.p1 - p0;
     const int nobs = s_bin.nobs;
-    ObsLin L;
+    double jp[2][3];
     double A0 = 0, A1 = 0, b0 = 0, b1 = 0;
     int q_of = 0;
     if (t < nobs) {
@@ -329,6 +329,7 @@ k_backsub(const double* __restrict__ tab, const double* __restrict__ pts,
       const long long p = pt[o];
       q_of = (int)(obs_start[p] - o0);
       const double w = wgt ? wgt[o] : 1.0;
+      ObsLin L;
       obs_linearize<false>(s_tab + c * CAMTAB, pts[3 * p], pts[3 * p + 1], pts[3 * p + 2], 0.0,
                            0.0, w, L);
       const double* gc = s_gc + c * NCP;
@@ -345,8 +346,12 @@ k_backsub(const double* __restrict__ tab, const double* __restrict__ pts,
         const double g = gt_p[3 * p + a];
         A0 = fma(L.Jp[0][a], g, A0);
         A1 = fma(L.Jp[1][a], g, A1);
-        s_tv[t * 3 + a] = fma(L.Jp[0][a], b0, L.Jp[1][a] * b1);   // J_p^T (J_c p_c)
+        jp[0][a] = L.Jp[0][a];
+        jp[1][a] = L.Jp[1][a];
       }
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+        s_tv[t * 3 + a] = fma(jp[0][a], b0, jp[1][a] * b1);   // J_p^T (J_c p_c)
     }
     __syncthreads();
     for (long long q = t; q < npts; q += LIN_THREADS) {
@@ -385,7 +390,7 @@ k_backsub(const double* __restrict__ tab, const double* __restrict__ pts,
     if (t < nobs) {
       const double* pp = s_pp + q_of * 3;
 #pragma unroll
-      for (int a = 0; a < 3; ++a) { b0 = fma(L.Jp[0][a], pp[a], b0); b1 = fma(L.Jp[1][a], pp[a], b1); }
+      for (int a = 0; a < 3; ++a) { b0 = fma(jp[0][a], pp[a], b0); b1 = fma(jp[1][a], pp[a], b1); }
       acc[0] = fma(A0, A0, fma(A1, A1, acc[0]));
       acc[1] = fma(A0, b0, fma(A1, b1, acc[1]));
       acc[2] = fma(b0, b0, fma(b1, b1, acc[2]));

@@ -91,15 +91,17 @@ __device__ __forceinline__ void project_tab(const double* __restrict__ T, double
   pv = fma(fd, y, T[10]);
 }
 
+// `live` = false turns the observation into an exact zero (w must be 0 too): the perspective
+// divide is masked so that no Inf/NaN can appear for a camera that does not see the point.
 template <bool WITH_RES>
 __device__ __forceinline__ void obs_linearize(const double* __restrict__ T, double X, double Y,
                                               double Z, double uo, double vo, double w,
-                                              ObsLin& o) {
+                                              ObsLin& o, bool live = true) {
   const double* R = T + CT_R;
   const double xc = fma(R[0], X, fma(R[1], Y, fma(R[2], Z, T[3])));
   const double yc = fma(R[3], X, fma(R[4], Y, fma(R[5], Z, T[4])));
   const double zc = fma(R[6], X, fma(R[7], Y, fma(R[8], Z, T[5])));
-  const double iz = 1.0 / zc;
+  const double iz = live ? 1.0 / zc : 0.0;
   const double x = xc * iz, y = yc * iz;
   const double n = x * x + y * y;
   const double f = T[6], k1 = T[7], k2 = T[8];

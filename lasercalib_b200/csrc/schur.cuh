@@ -58,7 +58,7 @@ struct SchurPlan {
 inline int pair_index(int j, int k) { return j * (j + 1) / 2 + k; }
 
 inline size_t schur_smem_bytes(int C, int pc, int nslots, int ndiag) {
-  return ((size_t)pc * nslots * Y_LD + (size_t)pc * ndiag * JC_LD + (size_t)pc * 6 +
+  return ((size_t)pc * nslots * Y_LD + (size_t)pc * ndiag * JC_LD + (size_t)pc * 2 +
           (size_t)C * CAMTAB) * 8 + 64;
 }
 
@@ -67,24 +67,28 @@ inline SchurPlan make_schur_plan(int C, int sm_count, size_t smem_limit) {
   pl.C = C;
   const int nb = (C + 1) / 2;
   const int nblocks = nb * (nb + 1) / 2;
-  pl.nkinds = (nblocks + SCHUR_MAX_HW - 1) / SCHUR_MAX_HW;
-  const int bpk = (nblocks + pl.nkinds - 1) / pl.nkinds;
   pl.npairs = C * (C + 1) / 2;
   pl.part_stride = (size_t)pl.npairs * 121 + (size_t)NCP * C;
   int b = 0, bj = 0, bk = 0;
-  pl.pc = 1 << 30;
-  for (int kd = 0; kd < pl.nkinds; ++kd) {
+  pl.pc = 0;
+  while (b < nblocks) {
     SchurKind K{};
     K.hw_base = (int)pl.hws.size();
     bool used[LCBA_MAX_CAMERAS] = {false}, isdiag[LCBA_MAX_CAMERAS] = {false};
     std::vector<std::pair<int, int>> blks;
-    for (int i = 0; i < bpk && b < nblocks; ++i, ++b) {
+    // greedy fill: a kind with an odd number of diagonal blocks needs one idle half-warp
+    int nd = 0;
+    while (b < nblocks) {
+      const int dg = (bj == bk) ? 1 : 0;
+      if ((int)blks.size() + 1 + ((nd + dg) & 1) > SCHUR_MAX_HW) break;
+      nd += dg;
       blks.push_back({bj, bk});
       for (int d = 0; d < 2; ++d) {
         if (2 * bj + d < C) used[2 * bj + d] = true;
         if (2 * bk + d < C) used[2 * bk + d] = true;
         if (bj == bk && 2 * bj + d < C) isdiag[2 * bj + d] = true;
       }
+      ++b;
       if (++bk > bj) { bk = 0; ++bj; }
     }
     int slot_of[LCBA_MAX_CAMERAS], dslot_of[LCBA_MAX_CAMERAS];
@@ -97,8 +101,17 @@ inline SchurPlan make_schur_plan(int C, int sm_count, size_t smem_limit) {
         K.slot_dslot[K.nslots] = (int8_t)dslot_of[c];
         K.slot_cam[K.nslots++] = (uint8_t)c;
       }
+    // diagonal duo blocks first and in pairs, so that a warp is either all-diagonal (3 pairs +
+    // the rank-2 U update) or all-regular (4 pairs): balanced work per warp
+    std::stable_sort(blks.begin(), blks.end(), [](const std::pair<int, int>& a, const std::pair<int, int>& b) {
+      return (a.first == a.second) > (b.first == b.second);
+    });
+    int ndblk = 0;
+    for (auto& bl : blks) ndblk += bl.first == bl.second;
+    if (ndblk & 1) blks.insert(blks.begin() + ndblk, std::make_pair(-1, -1));   // idle half-warp
     for (auto& bl : blks) {
       SchurHw h{};
+      if (bl.first < 0) { pl.hws.push_back(h); continue; }
       const int cj[2] = {2 * bl.first, 2 * bl.first + 1};
       const int ck[2] = {2 * bl.second, 2 * bl.second + 1};
       for (int d = 0; d < 2; ++d) {
@@ -124,7 +137,7 @@ inline SchurPlan make_schur_plan(int C, int sm_count, size_t smem_limit) {
     pl.max_slots = std::max(pl.max_slots, K.nslots);
     // points per stage: SCHUR_STAGES stages must fit shared memory
     {
-      const size_t per_pt = ((size_t)K.nslots * Y_LD + (size_t)K.ndiag * JC_LD + 6) * 8;
+      const size_t per_pt = ((size_t)K.nslots * Y_LD + (size_t)K.ndiag * JC_LD + 2) * 8;
       const size_t fixed = (size_t)C * CAMTAB * 8 + 64;
       const int sp = (int)((smem_limit - fixed) / (per_pt * SCHUR_STAGES));
       K.pad0 = std::max(1, std::min(16, sp));
@@ -133,7 +146,7 @@ inline SchurPlan make_schur_plan(int C, int sm_count, size_t smem_limit) {
                              schur_smem_bytes(C, K.pad0 * SCHUR_STAGES, K.nslots, K.ndiag));
     pl.kinds.push_back(K);
   }
-  pl.pc = 0;
+  pl.nkinds = (int)pl.kinds.size();
   pl.nslices = std::max(1, sm_count / pl.nkinds);
   return pl;
 }
@@ -158,21 +171,21 @@ __device__ __forceinline__ void st4(double* p, double a, double b, double c, dou
 }
 
 // Phase 1 for one (point, camera slot): Y = (Jc^T Jp) L^-T into Ys, Jc into Js (diagonal slots).
-// Invisible cameras get zeros so that phase 2 needs no per-pair visibility test.
-__device__ __noinline__ void schur_produce(const double* __restrict__ T, const double* __restrict__ X,
-                                           const double* __restrict__ li, double w, bool visible,
-                                           double* __restrict__ Y, double* __restrict__ Js) {
-  if (!visible) {
-#pragma unroll
-    for (int e = 0; e < 48; e += 4) st4(Y + e, 0.0, 0.0, 0.0, 0.0);
-    if (Js) {
-#pragma unroll
-      for (int e = 0; e < 32; e += 4) st4(Js + e, 0.0, 0.0, 0.0, 0.0);
-    }
-    return;
-  }
+// Invisible cameras produce exact zeros (w = 0, masked divide) so that phase 2 needs no
+// per-pair visibility test.  Branch-free: two of these are interleaved per producer thread.
+struct ProdIn {
+  const double* T;
+  double X[3], li[9], w;
+  double *Y, *Js;
+  bool live;
+};
+
+__device__ __forceinline__ void schur_produce(const ProdIn& in) {
   ObsLin L;
-  obs_linearize<false>(T, X[0], X[1], X[2], 0.0, 0.0, w, L);
+  obs_linearize<false>(in.T, in.X[0], in.X[1], in.X[2], 0.0, 0.0, in.w, L, in.live);
+  const double w = in.w;
+  const double* li = in.li;
+  double* Y = in.Y;
   double Q[2][3];
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
@@ -188,9 +201,12 @@ __device__ __noinline__ void schur_produce(const double* __restrict__ T, const d
     st4(Y + k * 16 + 0, y[0], y[1], y[2], 0.0);
     st4(Y + k * 16 + 4, y[3], y[4], y[5], 0.0);
     st4(Y + k * 16 + 8, y[6], y[7], y[8], 0.0);
-    st4(Y + k * 16 + 12, w * Q[0][k], w * Q[1][k], 0.0, 0.0);
+    // row 11 is padding for the 12x12 lane grid: it carries z = L^-1 g_p, so that column 11
+    // of the diagonal pair block accumulates -Y_j z = the reduced right-hand side for free
+    st4(Y + k * 16 + 12, w * Q[0][k], w * Q[1][k], li[6 + k], 0.0);
   }
-  if (Js) {
+  if (in.Js) {
+    double* Js = in.Js;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       st4(Js + i * 16 + 0, L.Jc[i][0], L.Jc[i][1], L.Jc[i][2], 0.0);
@@ -228,8 +244,8 @@ k_schur(const double* __restrict__ tab, const double* __restrict__ pts,
   const int tid = threadIdx.x;
   if (tid >= nthreads) return;          // uniform per warp (threads multiple of 32)
   const int nslots = K.nslots, ndiag = K.ndiag, SP = K.pad0, prod0 = K.qpr;
-  // per stage: Y[SP][nslots][Y_LD] J[SP][ndiag][JC_LD] z[SP][4] mask[SP] pad[SP] (even => 16 B)
-  const size_t stage_doubles = (size_t)SP * nslots * Y_LD + (size_t)SP * ndiag * JC_LD + SP * 6;
+  // per stage: Y[SP][nslots][Y_LD] J[SP][ndiag][JC_LD] mask[SP] pad[SP] (even => 16 B)
+  const size_t stage_doubles = (size_t)SP * nslots * Y_LD + (size_t)SP * ndiag * JC_LD + SP * 2;
   double* s_tab = s_dyn + SCHUR_STAGES * stage_doubles;      // C * CAMTAB
   enum { BAR_FULL = 2, BAR_EMPTY = 4, BAR_PROD = 6 };
 
@@ -255,28 +271,41 @@ k_schur(const double* __restrict__ tab, const double* __restrict__ pts,
       if (c >= nchunks) continue;
       double* s_Y = s_dyn + st * stage_doubles;
       double* s_J = s_Y + (size_t)SP * nslots * Y_LD;
-      double* s_z = s_J + (size_t)SP * ndiag * JC_LD;
-      unsigned long long* s_mask = reinterpret_cast<unsigned long long*>(s_z + SP * 4);
+      unsigned long long* s_mask =
+          reinterpret_cast<unsigned long long*>(s_J + (size_t)SP * ndiag * JC_LD);
       const long long q0 = pa + c * SP;
       const int npc = (int)min((long long)SP, pb - q0);
-      for (int idx = ptid; idx < npc * nslots; idx += nprod) {
-        const int q = idx / nslots, sl = idx - q * nslots;
-        const long long p = q0 + q;
-        const unsigned long long m = mask[p];
-        const int cam = K.slot_cam[sl];
-        const int ds = K.slot_dslot[sl];
-        const bool vis = (m >> cam) & 1ull;
-        double w = 1.0;
-        if (vis && wgt) w = wgt[(long long)obs_start[p] + __popcll(m & ((1ull << cam) - 1ull))];
-        schur_produce(s_tab + cam * CAMTAB, pts + 3 * p, Lz + p * 9, w, vis,
-                      s_Y + ((size_t)q * nslots + sl) * Y_LD,
-                      ds >= 0 ? s_J + ((size_t)q * ndiag + ds) * JC_LD : nullptr);
+      // two (point, slot) evaluations in flight per thread: loads first, then both chains
+      const int total = npc * nslots;
+      for (int base = ptid; base < total; base += 2 * nprod) {
+        ProdIn in[2];
+        bool have[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int idx = base + e * nprod;
+          have[e] = idx < total;
+          const int ii = have[e] ? idx : base;
+          const int q = ii / nslots, sl = ii - q * nslots;
+          const long long p = q0 + q;
+          const unsigned long long m = mask[p];
+          const int cam = K.slot_cam[sl];
+          const int ds = K.slot_dslot[sl];
+          in[e].live = (m >> cam) & 1ull;
+          in[e].w = 0.0;
+          if (in[e].live)
+            in[e].w = wgt ? wgt[(long long)obs_start[p] + __popcll(m & ((1ull << cam) - 1ull))] : 1.0;
+          in[e].T = s_tab + cam * CAMTAB;
+#pragma unroll
+          for (int a = 0; a < 3; ++a) in[e].X[a] = pts[3 * p + a];
+#pragma unroll
+          for (int a = 0; a < 9; ++a) in[e].li[a] = Lz[p * 9 + a];
+          in[e].Y = s_Y + ((size_t)q * nslots + sl) * Y_LD;
+          in[e].Js = ds >= 0 ? s_J + ((size_t)q * ndiag + ds) * JC_LD : nullptr;
+        }
+        schur_produce(in[0]);
+        if (have[1]) schur_produce(in[1]);
       }
-      for (int q = ptid; q < npc; q += nprod) {
-        s_mask[q] = mask[q0 + q];
-        const double* li = Lz + (q0 + q) * 9;
-        s_z[q * 4] = li[6]; s_z[q * 4 + 1] = li[7]; s_z[q * 4 + 2] = li[8];
-      }
+      for (int q = ptid; q < npc; q += nprod) s_mask[q] = mask[q0 + q];
       __threadfence_block();
       nbar_arrive(BAR_FULL + st, nthreads);
     }
@@ -295,23 +324,20 @@ k_schur(const double* __restrict__ tab, const double* __restrict__ pts,
     bm_j = (1ull << D.c[0]) | ((valid & 12u) ? (1ull << D.c[1]) : 0ull);
     bm_k = (1ull << D.c[2]) | ((valid & 10u) ? (1ull << D.c[3]) : 0ull);
   }
+  // all-diagonal warp: pairs 00, 10, 11 (+ U); all-regular warp: pairs 00, 01, 10, 11
+  const bool dwarp = __any_sync(0xffffffffu, diag != 0);
   double acc[4][9];
-  double rh[2][3];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 9; ++j) acc[i][j] = 0.0;
-#pragma unroll
-  for (int i = 0; i < 2; ++i)
-#pragma unroll
-    for (int j = 0; j < 3; ++j) rh[i][j] = 0.0;
 
   for (long long c = 0; c < nchunks; ++c) {
     const int st = (int)(c % SCHUR_STAGES);
     const double* s_Y = s_dyn + st * stage_doubles;
     const double* s_J = s_Y + (size_t)SP * nslots * Y_LD;
-    const double* s_z = s_J + (size_t)SP * ndiag * JC_LD;
-    const unsigned long long* s_mask = reinterpret_cast<const unsigned long long*>(s_z + SP * 4);
+    const unsigned long long* s_mask =
+        reinterpret_cast<const unsigned long long*>(s_J + (size_t)SP * ndiag * JC_LD);
     const int npc = (int)min((long long)SP, pb - (pa + c * SP));
     nbar_sync(BAR_FULL + st, nthreads);
     if (valid) {
@@ -329,19 +355,11 @@ k_schur(const double* __restrict__ tab, const double* __restrict__ pts,
           ld3(Yq + ok0 + k * 16, b0);
           ld3(Yq + ok1 + k * 16, b1);
           outer9<true>(acc[0], a0, b0);
-          outer9<true>(acc[1], a0, b1);
+          if (!dwarp) outer9<true>(acc[1], a0, b1);
           outer9<true>(acc[2], a1, b0);
           outer9<true>(acc[3], a1, b1);
-          if (diag) {
-            const double zk = s_z[q * 4 + k];
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-              rh[0][i] = fma(-a0[i], zk, rh[0][i]);
-              rh[1][i] = fma(-a1[i], zk, rh[1][i]);
-            }
-          }
         }
-        if (diag) {   // U_j = sum Jc^T Jc on the diagonal pairs
+        if (dwarp) {   // U_j = sum Jc^T Jc on the diagonal pairs
           const double* Jq = s_J + (size_t)q * ndiag * JC_LD;
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
@@ -374,7 +392,7 @@ k_schur(const double* __restrict__ tab, const double* __restrict__ pts,
           if (a < NCP && b < NCP) blk[a * NCP + b] = acc[pr][3 * i + j];
         }
     }
-    if (cc == 0) {
+    if (cc == 3) {   // column 11 of the diagonal pair blocks = reduced right-hand side
       double* rout = out + (size_t)npairs * 121;
 #pragma unroll
       for (int d = 0; d < 2; ++d) {
@@ -382,7 +400,7 @@ k_schur(const double* __restrict__ tab, const double* __restrict__ pts,
         const int cj = D.c[d];
 #pragma unroll
         for (int i = 0; i < 3; ++i)
-          if (3 * rr + i < NCP) rout[cj * NCP + 3 * rr + i] = rh[d][i];
+          if (3 * rr + i < NCP) rout[cj * NCP + 3 * rr + i] = acc[3 * d][3 * i + 2];
       }
     }
   }
