@@ -1,0 +1,60 @@
+"""Worker of tests/test_gpu_dist.py (launched by torchrun, one rank per GPU): the point-sharded
+NCCL solve must reproduce the single-GPU solve."""
+import os
+import sys
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+
+import torch  # noqa: E402
+
+from lasercalib_b200 import dist as D  # noqa: E402
+from lasercalib_b200._cabi import Engine  # noqa: E402
+from lasercalib_b200.pySBA import PySBA  # noqa: E402
+from lasercalib_b200.synth import make_rig  # noqa: E402
+
+
+def main():
+    rank, ws, local = D.init_from_env()
+    assert ws > 1
+    torch.cuda.set_device(local)
+    pb = make_rig("ring24", 20000, seed=3, variant="volume", p_vis=0.6)
+    # single-GPU reference on every rank's own device
+    eng = Engine(local)
+    eng.set_problem(pb["cams0"], pb["pts0"], pb["points_2d"], pb["camera_ind"], pb["point_ind"])
+    lin1 = eng.linearize(1e-6)
+    res1, trace1 = eng.solve(ftol=1e-4)
+    cams1, pts1 = eng.get_params()
+    eng.close()
+    # sharded: reduced camera system
+    sh = D.shard_problem(pb["pts0"], pb["points_2d"], pb["camera_ind"], pb["point_ind"], None, rank, ws)
+    e2 = Engine(local)
+    e2.set_problem(pb["cams0"], sh["pts"], sh["points_2d"], sh["camera_ind"], sh["point_ind"])
+    D.connect_engine(e2)
+    lin2 = e2.linearize(1e-6)
+    assert np.abs(lin2["S"] - lin1["S"]).max() <= 1e-12 * np.abs(lin1["S"]).max()
+    assert np.abs(lin2["rhs"] - lin1["rhs"]).max() <= 1e-11 * np.abs(lin1["rhs"]).max()
+    np.testing.assert_allclose(lin2["cost"], lin1["cost"], rtol=1e-13)
+    e2.close()
+    # sharded through the drop-in API
+    sba = PySBA(pb["cams0"].copy(), pb["pts0"].copy(), pb["points_2d"], pb["camera_ind"], pb["point_ind"])
+    res2 = sba.bundleAdjust(1e-4, verbose=0)
+    assert res2.nfev == res1.nfev and res2.status == res1.status, (res2.nfev, res1.nfev)
+    np.testing.assert_allclose(res2.cost, res1.cost, rtol=1e-10)
+    np.testing.assert_allclose(sba.cameraArray, cams1, rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(sba.points3D, pts1, rtol=1e-7, atol=1e-7)
+    # identical decisions on every rank
+    t = torch.tensor([res2.cost, float(res2.nfev)], dtype=torch.float64, device="cuda")
+    lo, hi = t.clone(), t.clone()
+    torch.distributed.all_reduce(lo, op=torch.distributed.ReduceOp.MIN)
+    torch.distributed.all_reduce(hi, op=torch.distributed.ReduceOp.MAX)
+    assert torch.equal(lo, hi)
+    torch.distributed.barrier()
+    torch.distributed.destroy_process_group()
+    print("rank %d ok" % rank)
+
+
+if __name__ == "__main__":
+    main()

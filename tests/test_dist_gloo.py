@@ -1,0 +1,73 @@
+"""N > 1 host logic on CPU: world_size-2 (and 3) gloo jobs (no GPU)."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from lasercalib_b200 import dist as D
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _run_world(ws, extra_env=None):
+    port = _free_port()
+    procs = []
+    for r in range(ws):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(ws), LOCAL_RANK=str(r),
+                   MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1",
+                   CUDA_VISIBLE_DEVICES="")
+        env.update(extra_env or {})
+        procs.append(subprocess.Popen([sys.executable, os.path.join(REPO, "tests", "_dist_worker.py")],
+                                      env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = []
+    for p in procs:
+        try:
+            out, _ = p.communicate(timeout=240)
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            raise
+        outs.append(out)
+    for r, (p, out) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, "rank %d failed:\n%s" % (r, out[-3000:])
+        assert "rank %d ok" % r in out
+
+
+def test_two_rank_gloo_shard_reduce_gather():
+    _run_world(2)
+
+
+def test_three_rank_gloo_unsorted_observations():
+    _run_world(3, {"LCBA_TEST_SHUFFLE": "1"})
+
+
+def test_shard_bounds_properties():
+    rng = np.random.default_rng(0)
+    P = 1000
+    counts = rng.integers(0, 25, P)
+    counts[100:140] = 0                        # points nobody sees
+    pi = np.repeat(np.arange(P), counts)
+    for ws in (1, 2, 4, 8):
+        b = D.shard_bounds(pi, P, ws)
+        assert b[0] == 0 and b[-1] == P and len(b) == ws + 1 and np.all(np.diff(b) >= 0)
+        per = [int(((pi >= b[r]) & (pi < b[r + 1])).sum()) for r in range(ws)]
+        assert sum(per) == pi.size
+        assert max(per) <= pi.size / ws + 25
+    # degenerate: fewer points than ranks
+    b = D.shard_bounds(np.array([0, 0, 1]), 2, 8)
+    assert b[0] == 0 and b[-1] == 2 and np.all(np.diff(b) >= 0)
+
+
+def test_world_defaults_to_single_process():
+    assert D.world() == (0, 1, 0)
