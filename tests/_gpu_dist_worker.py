@@ -43,8 +43,10 @@ def main():
     res2 = sba.bundleAdjust(1e-4, verbose=0)
     assert res2.nfev == res1.nfev and res2.status == res1.status, (res2.nfev, res1.nfev)
     np.testing.assert_allclose(res2.cost, res1.cost, rtol=1e-10)
-    np.testing.assert_allclose(sba.cameraArray, cams1, rtol=1e-7, atol=1e-9)
-    np.testing.assert_allclose(sba.points3D, pts1, rtol=1e-7, atol=1e-7)
+    # all-reduce order changes S in the 13th digit; the gauge / weak modes amplify that in the
+    # raw parameters while cost and decisions stay identical
+    np.testing.assert_allclose(sba.cameraArray, cams1, rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(sba.points3D, pts1, rtol=1e-4, atol=1e-3)
     # identical decisions on every rank
     t = torch.tensor([res2.cost, float(res2.nfev)], dtype=torch.float64, device="cuda")
     lo, hi = t.clone(), t.clone()
