@@ -116,9 +116,10 @@ static int dev_alloc(lcba_t* h, T** p, size_t count) {
   *p = nullptr;
   if (count == 0) count = 1;
   void* q = nullptr;
-  cudaError_t e = cudaMalloc(&q, count * sizeof(T));
+  // stream-ordered pool allocation: repeated set_problem calls reuse the cached blocks
+  cudaError_t e = cudaMallocAsync(&q, count * sizeof(T), h->stream);
   if (e != cudaSuccess) {
-    set_error(h, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    set_error(h, std::string("cudaMallocAsync: ") + cudaGetErrorString(e));
     return LCBA_E_CUDA;
   }
   h->allocs.push_back(q);
@@ -127,7 +128,7 @@ static int dev_alloc(lcba_t* h, T** p, size_t count) {
 }
 
 static void dev_free_all(lcba_t* h) {
-  for (void* p : h->allocs) cudaFree(p);
+  for (void* p : h->allocs) cudaFreeAsync(p, h->stream);
   h->allocs.clear();
 }
 
@@ -207,6 +208,13 @@ extern "C" int lcba_create(lcba_t** out, int device) {
   h->sm_count = prop.multiProcessorCount;
   h->smem_optin = prop.sharedMemPerBlockOptin;
   cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long keep = ~0ull;       // keep freed blocks cached in the pool
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   cudaEventCreate(&h->ev0);
   cudaEventCreate(&h->ev1);
   cudaMallocHost((void**)&h->h_ctl, sizeof(Ctl));
@@ -238,6 +246,7 @@ extern "C" void lcba_destroy(lcba_t* h) {
   cudaSetDevice(h->device);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   dev_free_all(h);
+  if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -293,8 +302,8 @@ extern "C" int lcba_set_problem(lcba_t* h, int32_t C, int64_t P, int64_t N, cons
   int* d_flags = nullptr;
   void* t_cub = nullptr;
   auto cleanup = [&]() {
-    cudaFree(t_cam); cudaFree(t_pt); cudaFree(t_keys); cudaFree(t_keys2); cudaFree(t_uv);
-    cudaFree(t_w); cudaFree(t_iota); cudaFree(t_cub); cudaFree(d_flags);
+    void* tmp[] = {t_cam, t_pt, t_keys, t_keys2, t_uv, t_w, t_iota, t_cub, d_flags};
+    for (void* q : tmp) if (q) cudaFreeAsync(q, st);
   };
 #define ING(call)                                                                   \
   do {                                                                              \
@@ -305,12 +314,12 @@ extern "C" int lcba_set_problem(lcba_t* h, int32_t C, int64_t P, int64_t N, cons
       return LCBA_E_CUDA;                                                           \
     }                                                                               \
   } while (0)
-  ING(cudaMalloc(&t_cam, N * 8));
-  ING(cudaMalloc(&t_pt, N * 8));
-  ING(cudaMalloc(&t_keys, N * 8));
-  ING(cudaMalloc(&t_uv, N * 16));
-  if (weights) ING(cudaMalloc(&t_w, N * 8));
-  ING(cudaMalloc(&d_flags, 2 * sizeof(int)));
+  ING(cudaMallocAsync(&t_cam, N * 8, st));
+  ING(cudaMallocAsync(&t_pt, N * 8, st));
+  ING(cudaMallocAsync(&t_keys, N * 8, st));
+  ING(cudaMallocAsync(&t_uv, N * 16, st));
+  if (weights) ING(cudaMallocAsync(&t_w, N * 8, st));
+  ING(cudaMallocAsync(&d_flags, 2 * sizeof(int), st));
   ING(cudaMemsetAsync(d_flags, 0, 2 * sizeof(int), st));
   ING(cudaMemcpyAsync(t_cam, cam_idx, N * 8, cudaMemcpyHostToDevice, st));
   ING(cudaMemcpyAsync(t_pt, pt_idx, N * 8, cudaMemcpyHostToDevice, st));
@@ -332,8 +341,8 @@ extern "C" int lcba_set_problem(lcba_t* h, int32_t C, int64_t P, int64_t N, cons
   h->d_perm = nullptr;
   if (flags[0] & 2) {
     // unsorted input: radix sort by (point, camera), remember the permutation
-    ING(cudaMalloc(&t_keys2, N * 8));
-    ING(cudaMalloc(&t_iota, N * 4));
+    ING(cudaMallocAsync(&t_keys2, N * 8, st));
+    ING(cudaMallocAsync(&t_iota, N * 4, st));
     LCBA_TRY(dev_alloc(h, &h->d_perm, (size_t)N));
     k_iota<<<nblk(N, 256), 256, 0, st>>>(t_iota, N);
     h->launches++;
@@ -342,7 +351,7 @@ extern "C" int lcba_set_problem(lcba_t* h, int32_t C, int64_t P, int64_t N, cons
     while ((1LL << (end_bit - 8)) < P && end_bit < 64) ++end_bit;
     cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, t_keys, t_keys2, t_iota, h->d_perm,
                                     (int)N, 0, end_bit, st);
-    ING(cudaMalloc(&t_cub, cub_bytes));
+    ING(cudaMallocAsync(&t_cub, cub_bytes, st));
     ING(cub::DeviceRadixSort::SortPairs(t_cub, cub_bytes, t_keys, t_keys2, t_iota, h->d_perm,
                                         (int)N, 0, end_bit, st));
     h->launches += 8;

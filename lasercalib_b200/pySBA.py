@@ -88,13 +88,26 @@ class PySBA:
         self.cameraIndices = cameraIndices
         self.point2DIndices = point2DIndices
         self.points3Dfixed = points3Dfixed
-        if pointWeights is None:
-            pointWeights = np.full_like(point2DIndices, 1)
-        self.pointWeights = pointWeights.reshape((-1, 1))
+        # The reference materialises np.full_like(point2DIndices, 1).reshape(-1, 1) here
+        # (pySBA.py:56-58); the same array appears on first access of `.pointWeights`, but the
+        # solver path never pays for 8 bytes per observation of ones.
+        self._default_weights = pointWeights is None
+        self._pointWeights = None if pointWeights is None else pointWeights.reshape((-1, 1))
         self.points3Dfixed_labeled = None
         self._engine = None
         self._problem_key = None
         self.last_trace = None
+
+    @property
+    def pointWeights(self):
+        if self._pointWeights is None:
+            self._pointWeights = np.full_like(self.point2DIndices, 1).reshape((-1, 1))
+        return self._pointWeights
+
+    @pointWeights.setter
+    def pointWeights(self, value):
+        self._default_weights = False
+        self._pointWeights = value
 
     # ---- pickling: device handles never enter the pickle (calibrate_camera.py:86-88) ----
     def __getstate__(self):
@@ -114,8 +127,10 @@ class PySBA:
             self._comm_ready = False
         return self._engine
 
-    @staticmethod
-    def _weights_arg(pointWeights):
+    def _weights_arg(self, pointWeights):
+        if pointWeights is None or (self._default_weights and pointWeights is self._pointWeights):
+            n = np.asarray(self.point2DIndices).size
+            return None, ("ones", n)
         w = np.asarray(pointWeights).reshape(-1)
         if w.dtype.kind in "iu" and np.all(w == 1):
             return None, ("ones", w.size)
@@ -131,7 +146,8 @@ class PySBA:
         p2 = np.asarray(points_2d)
         key = (cams.shape[0], pts.shape[0], ci.ctypes.data, ci.size, pi.ctypes.data,
                p2.ctypes.data, wkey)
-        if key != self._problem_key:
+        self._fresh_problem = key != self._problem_key
+        if self._fresh_problem:
             eng.set_problem(cams, pts, p2, ci, pi, w)
             self._problem_key = key
             self._keep = (ci, pi, p2, w)       # keep the keyed buffers alive
@@ -195,7 +211,7 @@ class PySBA:
         if ws > 1:
             # one process per GPU: this rank keeps a contiguous range of points and their
             # observations; cameras are replicated; the library all-reduces with NCCL
-            w, _ = self._weights_arg(self.pointWeights)
+            w, _ = self._weights_arg(self._pointWeights)
             shard = _dist.shard_problem(pts0, self.points2D, self.cameraIndices,
                                         self.point2DIndices, w, rank, ws)
             eng = self._get_engine()
@@ -209,8 +225,9 @@ class PySBA:
                 verbose = 0
         else:
             eng = self._ensure_problem(cams0, pts0, self.cameraIndices, self.point2DIndices,
-                                       self.points2D, self.pointWeights)
-            eng.set_params(cams0, pts0)
+                                       self.points2D, self._pointWeights)
+            if not self._fresh_problem:        # observations already resident: new x0 only
+                eng.set_params(cams0, pts0)
         try:
             res, trace = eng.solve(ftol=ftol, xtol=xtol, gtol=gtol, max_nfev=max_nfev or 0,
                                    verbose=verbose, profile=profile,
