@@ -29,7 +29,7 @@ if REPO not in sys.path:
 
 METRIC = "LM_iters_per_sec"
 UNIT = "iter/s"
-FP64_PEAK_FALLBACK_TFLOPS = 33.9   # DFMA peak measured on this pool (profiles/r01_fp64_peak.txt)
+FP64_PEAK_FALLBACK_TFLOPS = 37.1   # highest FP64 rate measured on this pool (profiles/r01_fp64_peak.txt)
 HBM_FALLBACK_GBS = 6650.0          # B200_PROFILING.md fallback
 
 
@@ -277,7 +277,7 @@ def main():
                 "peak": fp64_peak, "unit": "TFLOP/s", "frac": fl / ms_schur * 1e-9 / fp64_peak,
                 "traffic": None, "flop_per_launch": fl, "ms_per_launch": ms_schur,
                 "share_of_step": prof["schur"]["total_ms"] / kern_total,
-                "peak_source": "DFMA chain microbenchmark on this pool (profiles/r01_fp64_peak.txt)"}
+                "peak_source": "DFMA/DMMA microbenchmarks on this pool (profiles/r01_fp64_peak.txt)"}
     jac_bytes = 264.0 * n_loc + 24.0 * p_loc
     roof_m1 = {"kernel": "k_jacobian_blocks", "bound": "hbm", "achieved": jac_bytes / ms_jac * 1e-6,
                "peak": hbm_peak, "unit": "GB/s", "frac": jac_bytes / ms_jac * 1e-6 / hbm_peak,

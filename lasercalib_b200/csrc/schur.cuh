@@ -66,30 +66,64 @@ inline SchurPlan make_schur_plan(int C, int sm_count, size_t smem_limit) {
   SchurPlan pl;
   pl.C = C;
   const int nb = (C + 1) / 2;
-  const int nblocks = nb * (nb + 1) / 2;
   pl.npairs = C * (C + 1) / 2;
   pl.part_stride = (size_t)pl.npairs * 121 + (size_t)NCP * C;
-  int b = 0, bj = 0, bk = 0;
+  // Partition the lower-triangular duo-block matrix into kinds.  Greedy clustering over camera
+  // duos: a kind keeps a duo set D and takes every free block inside D x D; when none is left it
+  // adds the duo that unlocks the most free blocks.  Kinds become compact cliques / rectangles
+  // (few cameras each), so their producers compute few (point, camera) Jacobians.
+  std::vector<std::vector<char>> freeb(nb, std::vector<char>(nb, 0));
+  size_t nfree = 0;
+  for (int j = 0; j < nb; ++j)
+    for (int k = 0; k <= j; ++k) { freeb[j][k] = 1; ++nfree; }
   pl.pc = 0;
-  while (b < nblocks) {
+  while (nfree > 0) {
     SchurKind K{};
     K.hw_base = (int)pl.hws.size();
     bool used[LCBA_MAX_CAMERAS] = {false}, isdiag[LCBA_MAX_CAMERAS] = {false};
+    std::vector<char> inD(nb, 0);
     std::vector<std::pair<int, int>> blks;
-    // greedy fill: a kind with an odd number of diagonal blocks needs one idle half-warp
     int nd = 0;
-    while (b < nblocks) {
+    bool full = false;
+    while (nfree > 0 && !full) {
+      // 1. a free block inside D x D (row-major)
+      int bj = -1, bk = -1;
+      for (int j = 0; j < nb && bj < 0; ++j) {
+        if (!inD[j]) continue;
+        for (int k = 0; k <= j; ++k)
+          if (inD[k] && freeb[j][k]) { bj = j; bk = k; break; }
+      }
+      if (bj < 0) {
+        // 2. grow D by the duo that unlocks the most free blocks
+        int best = -1, gain_best = 0;
+        for (int d = 0; d < nb; ++d) {
+          if (inD[d]) continue;
+          int gain = freeb[d][d] ? 1 : 0;
+          for (int x = 0; x < nb; ++x)
+            if (inD[x]) gain += (x < d) ? freeb[d][x] : freeb[x][d];
+          if (gain > gain_best) { gain_best = gain; best = d; }
+        }
+        if (best < 0) {   // D empty or exhausted: seed with the first free block
+          for (int j = 0; j < nb && best < 0; ++j)
+            for (int k = 0; k <= j; ++k)
+              if (freeb[j][k]) { inD[j] = 1; inD[k] = 1; best = j; break; }
+        } else {
+          inD[best] = 1;
+        }
+        continue;
+      }
       const int dg = (bj == bk) ? 1 : 0;
-      if ((int)blks.size() + 1 + ((nd + dg) & 1) > SCHUR_MAX_HW) break;
+      // a kind with an odd number of diagonal blocks needs one idle half-warp
+      if ((int)blks.size() + 1 + ((nd + dg) & 1) > SCHUR_MAX_HW) { full = true; break; }
       nd += dg;
+      freeb[bj][bk] = 0;
+      --nfree;
       blks.push_back({bj, bk});
       for (int d = 0; d < 2; ++d) {
         if (2 * bj + d < C) used[2 * bj + d] = true;
         if (2 * bk + d < C) used[2 * bk + d] = true;
         if (bj == bk && 2 * bj + d < C) isdiag[2 * bj + d] = true;
       }
-      ++b;
-      if (++bk > bj) { bk = 0; ++bj; }
     }
     int slot_of[LCBA_MAX_CAMERAS], dslot_of[LCBA_MAX_CAMERAS];
     K.nslots = 0;
