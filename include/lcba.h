@@ -70,7 +70,9 @@ typedef struct lcba_options {
   int32_t verbose;    /* 2: keep a per-iteration trace (the host prints scipy's table) */
   int32_t profile;    /* 1: bracket every kernel launch with CUDA events (lcba_get_profile) */
   int32_t max_iterations; /* >0: stop after this many outer iterations (bench: time exactly K) */
-  int32_t reserved[5];
+  int32_t fix_cameras;    /* 1: optimise the 3-D points only (PySBA.bundleAdjust_nocam,
+                             pySBA.py:237-250): x = points, cameras stay at their values */
+  int32_t reserved[4];
 } lcba_options;
 
 /* One row of scipy's verbose=2 table (_lsq/common.py:545-563). */

@@ -122,11 +122,15 @@ __device__ inline void ctl_solve_subspace(Ctl* c) {
 __global__ void __launch_bounds__(256)
 k_ctl_lin(const double* __restrict__ camsum, const double* __restrict__ cams,
           double* __restrict__ scl_c, double* __restrict__ gt_c, double* __restrict__ g_c, int C,
-          Ctl* __restrict__ ctl, int first) {
+          Ctl* __restrict__ ctl, int first, int fix_cameras) {
   __shared__ double s_red[32];
   double gh2 = 0, xs2 = 0, x2 = 0, gmax = 0;
   for (int i = threadIdx.x; i < C * NCP; i += blockDim.x) {
     const int c = i / NCP, a = i % NCP;
+    if (fix_cameras) {          // cameras are constants: no gradient, no scale, no norm share
+      scl_c[i] = 1.0; g_c[i] = 0.0; gt_c[i] = 0.0;
+      continue;
+    }
     const double g = camsum[c * 22 + a];
     double s = sqrt(camsum[c * 22 + 11 + a]);
     if (first) { if (s == 0.0) s = 1.0; } else s = fmax(s, scl_c[i]);

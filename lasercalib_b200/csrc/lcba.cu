@@ -103,6 +103,7 @@ struct lcba_handle {
   // comm
   ncclComm_t comm = nullptr;
   int rank = 0, nranks = 1;
+  int fix_cameras = 0;
 };
 
 static std::string g_last_error;
@@ -594,7 +595,7 @@ static int pass_linearize(lcba_t* h, int first) {
                                                              h->d_camsum + C * CAMSUM, 1));
   LCBA_TRY(allreduce(h, h->d_camsum, (size_t)C * CAMSUM + 1, NCCL_SUM));
   KL(h, "ctl", k_ctl_lin<<<1, 256, 0, h->stream>>>(h->d_camsum, h->d_cams[w], h->d_scl_c, h->d_gt_c,
-                                                   h->d_g_c, C, h->d_ctl, first));
+                                                   h->d_g_c, C, h->d_ctl, first, h->fix_cameras));
   KL(h, "point_prep", k_point_prep<<<h->pt_grid, 256, 0, h->stream>>>(
         h->d_Vg, h->d_pts[w], h->d_scl_p, h->d_gt_p, h->P, first, h->d_part));
   KL(h, "reduce", k_reduce_scalars<<<PP_K, 256, 0, h->stream>>>(h->d_part, h->pt_grid, PP_K, h->d_red, 3));
@@ -789,7 +790,8 @@ extern "C" int lcba_solve(lcba_t* h, const lcba_options* opt_in, lcba_result* re
     LCBA_CUDA(h, cudaStreamSynchronize(h->stream));
     h->P_total = (long long)(v + 0.5);
   }
-  const long long n_total = (long long)h->C * NCP + 3 * h->P_total;
+  h->fix_cameras = opt.fix_cameras ? 1 : 0;
+  const long long n_total = (h->fix_cameras ? 0 : (long long)h->C * NCP) + 3 * h->P_total;
   const long long max_nfev = opt.max_nfev > 0 ? opt.max_nfev : 100 * n_total;
 
   cudaEvent_t t0, t1;
@@ -824,13 +826,21 @@ extern "C" int lcba_solve(lcba_t* h, const lcba_options* opt_in, lcba_result* re
     if (opt.max_iterations > 0 && iteration >= opt.max_iterations) break;
 
     LCBA_TRY(pass_jdot(h));
-    LCBA_TRY(pass_schur(h, nullptr));
+    if (h->fix_cameras) {
+      // points only: the normal equations are block diagonal, p_p = (V + lam Dp^2)^-1 g_p
+      KL(h, "point_factor", k_point_factor_ctl<<<nblk(h->P, 256), 256, 0, h->stream>>>(
+            h->d_Vg, h->d_scl_p, h->d_ctl, h->P, h->d_Lz));
+      LCBA_CUDA(h, cudaMemsetAsync(h->d_pc, 0, (size_t)h->C * NCP * 8, h->stream));
+      LCBA_CUDA(h, cudaMemsetAsync(h->d_fail, 0, sizeof(int), h->stream));
+    } else {
+      LCBA_TRY(pass_schur(h, nullptr));
+    }
     double mu = 0.0;
     bool have_trial = false;
     actual = -1.0;
     int term = -1;
     while (true) {   // Cholesky retry loop (extra camera damping on breakdown)
-      LCBA_TRY(pass_camera_solve(h, mu));
+      if (!h->fix_cameras) LCBA_TRY(pass_camera_solve(h, mu));
       LCBA_TRY(pass_backsub(h));
       LCBA_TRY(pass_trial(h));
       LCBA_TRY(read_ctl(h));
@@ -957,6 +967,7 @@ extern "C" int lcba_linearize(lcba_t* h, double lam, double* S_out, double* rhs_
   memset(&init, 0, sizeof(init));
   init.term = -1;
   LCBA_CUDA(h, cudaMemcpyAsync(h->d_ctl, &init, sizeof(Ctl), cudaMemcpyHostToDevice, h->stream));
+  h->fix_cameras = 0;
   LCBA_TRY(pass_linearize(h, 1));
   LCBA_TRY(pass_schur(h, &lam));
   const int n = h->C * NCP;

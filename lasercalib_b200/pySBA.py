@@ -195,7 +195,7 @@ class PySBA:
 
     # ---- solver (pySBA.py:132-147) ----
     def bundleAdjust(self, ftol=1e-4, xtol=1e-8, gtol=1e-8, max_nfev=None, verbose=2,
-                     profile=False, max_iterations=0):
+                     profile=False, max_iterations=0, _fix_cameras=False):
         """Returns the bundle adjusted parameters (scipy ``OptimizeResult`` layout) and
         stores them on ``self.cameraArray`` / ``self.points3D``.
 
@@ -231,7 +231,7 @@ class PySBA:
         try:
             res, trace = eng.solve(ftol=ftol, xtol=xtol, gtol=gtol, max_nfev=max_nfev or 0,
                                    verbose=verbose, profile=profile,
-                                   max_iterations=max_iterations)
+                                   max_iterations=max_iterations, fix_cameras=_fix_cameras)
         except _cabi.LcbaError as e:
             if e.code == -5:
                 raise ValueError("Residuals are not finite in the initial point.") from e
@@ -244,6 +244,8 @@ class PySBA:
         cams, pts = eng.get_params()
         if shard is not None:
             pts = _dist.allgather_rows(pts, shard["bounds"])
+        if _fix_cameras:
+            return self._finish_nocam(eng, res, pts, shard, verbose)
         x = np.hstack((cams.ravel(), pts.ravel()))
         out = BAResult(x=x, cost=res.cost, optimality=res.optimality,
                        active_mask=np.zeros_like(x), nfev=int(res.nfev), njev=int(res.njev),
@@ -295,8 +297,34 @@ class PySBA:
     def bundle_adjustment_camonly(self, ftol=1e-4):
         self._next_row("bundle_adjustment_camonly")
 
+    def _finish_nocam(self, eng, res, pts, shard, verbose):
+        x = pts.ravel().copy()
+        out = BAResult(x=x, cost=res.cost, optimality=res.optimality,
+                       active_mask=np.zeros_like(x), nfev=int(res.nfev), njev=int(res.njev),
+                       status=int(res.status))
+        out["message"] = TERMINATION_MESSAGES[int(res.status)]
+        out["success"] = int(res.status) > 0
+        out["solve_ms"] = res.solve_ms
+        out["nit"] = int(res.iterations)
+        out["gpu_launches"] = int(res.gpu_launches)
+        out.set_lazy("fun", lambda: eng.residuals(None)[0])
+        if shard is None:
+            nc = self.cameraArray.shape[0] * N_CAM_PARAMS
+            out.set_lazy("grad", lambda: eng.grad()[nc:])
+        else:
+            out["fun_obs_index"] = shard["obs_sel"]
+        if verbose >= 1:
+            print(out["message"])
+            print("Function evaluations {}, initial cost {:.4e}, final cost {:.4e}, "
+                  "first-order optimality {:.2e}.".format(out["nfev"], res.initial_cost,
+                                                          res.cost, res.optimality))
+        self.points3D = x.reshape((-1, 3))
+        return out
+
     def bundleAdjust_nocam(self, ftol=1e-7):
-        self._next_row("bundleAdjust_nocam")
+        """Returns the optimized 3d positions given current camera parameters, without
+        adjusting the camera parameters themselves (pySBA.py:237-250): x = points only."""
+        return self.bundleAdjust(ftol, _fix_cameras=True)
 
     def bundleAdjust_sharedcam(self, ftol=1e-6):
         self._next_row("bundleAdjust_sharedcam")

@@ -472,6 +472,116 @@ def trf_exact(cams, pts, points_2d, camera_indices, point_indices, weights=None,
     return res
 
 
+def fun_nocam(params, camera_params, n_points, camera_indices, point_indices, points_2d, weights):
+    """Residuals with the 3-D points as the only unknowns (pySBA.py:226-235)."""
+    pts = params.reshape((n_points, 3))
+    uv = project(pts[point_indices], camera_params[camera_indices])
+    return (weights * (uv - points_2d)).ravel()
+
+
+def bundle_adjust_nocam(cams, pts, points_2d, camera_indices, point_indices, weights=None,
+                        ftol=1e-7, verbose=0, **ls_kwargs):
+    """The reference's ``bundleAdjust_nocam`` (pySBA.py:237-250) through scipy."""
+    P = pts.shape[0]
+    if weights is None:
+        weights = default_weights(point_indices)
+    weights = np.asarray(weights).reshape(-1, 1)
+    N = point_indices.size
+    cols = (point_indices[:, None] * 3 + np.arange(3))[:, None, :].repeat(2, axis=1)
+    A = csr_matrix((np.ones(cols.size, dtype=int), cols.ravel(),
+                    np.arange(0, 6 * N + 1, 3, dtype=np.int64)), shape=(2 * N, 3 * P))
+    return least_squares(fun_nocam, pts.ravel(), jac_sparsity=A, verbose=verbose, x_scale="jac",
+                         ftol=ftol, method="trf", jac="3-point",
+                         args=(cams, P, camera_indices, point_indices, points_2d, weights),
+                         **ls_kwargs)
+
+
+def trf_exact_nocam(cams, pts, points_2d, camera_indices, point_indices, weights=None,
+                    ftol=1e-7, xtol=1e-8, gtol=1e-8, max_nfev=None):
+    """``trf_exact`` with the cameras held fixed (x = points): the damped normal equations are
+    block diagonal, p_p = (V_p + reg_term Dp^2)^-1 g_p."""
+    from numpy.linalg import norm
+    from scipy.linalg import qr
+    from scipy.optimize._lsq.common import (check_termination, minimize_quadratic_1d,
+                                            solve_trust_region_2d, update_tr_radius)
+    C, P = cams.shape[0], pts.shape[0]
+    if weights is None:
+        weights = default_weights(point_indices)
+    weights = np.asarray(weights).reshape(-1, 1)
+    args = (cams, P, camera_indices, point_indices, points_2d, weights)
+    x = pts.ravel().astype(np.float64)
+
+    def lin(xv):
+        fv = fun_nocam(xv, *args)
+        _, _, Jp = jacobian_blocks(cams, xv.reshape(P, 3), camera_indices, point_indices, weights)
+        V = np.zeros((P, 3, 3))
+        gp = np.zeros((P, 3))
+        np.add.at(V, point_indices, np.einsum("nia,nib->nab", Jp, Jp))
+        np.add.at(gp, point_indices, np.einsum("nia,ni->na", Jp, fv.reshape(-1, 2)))
+        return fv, Jp, V, gp
+
+    f, Jp, V, gp = lin(x)
+    if not np.all(np.isfinite(f)):
+        raise ValueError("Residuals are not finite in the initial point.")
+    nfev = njev = 1
+    cost = 0.5 * f @ f
+    g = gp.ravel()
+    scale_inv = np.sqrt(np.einsum("paa->pa", V)).ravel()
+    scale_inv[scale_inv == 0] = 1
+    Delta = norm(x * scale_inv) or 1.0
+    if max_nfev is None:
+        max_nfev = x.size * 100
+    Jdot = lambda v: np.einsum("nia,na->ni", Jp, v.reshape(P, 3)[point_indices])
+    status, trace = None, []
+    g_norm = norm(g, ord=np.inf)
+    while True:
+        g_norm = norm(g, ord=np.inf)
+        if g_norm < gtol:
+            status = 1
+        trace.append(cost)
+        if status is not None or nfev == max_nfev:
+            break
+        d = 1 / scale_inv
+        g_h = d * g
+        Jg = Jdot(d * g_h)
+        a, b = 0.5 * np.sum(Jg * Jg), -g_h @ g_h
+        reg = -minimize_quadratic_1d(a, b, 0, Delta / norm(g_h))[1] / Delta**2
+        Vd = V.copy()
+        Vd[:, np.arange(3), np.arange(3)] += reg * scale_inv.reshape(P, 3) ** 2
+        p = np.linalg.solve(Vd, gp[:, :, None])[:, :, 0].ravel()
+        Sq, _ = qr(np.vstack((g_h, p * scale_inv)).T, mode="economic")
+        JS = np.stack([Jdot(d * Sq[:, 0]).ravel(), Jdot(d * Sq[:, 1]).ravel()], axis=1)
+        B_S, g_S = JS.T @ JS, Sq.T @ g_h
+        actual = -1
+        while actual <= 0 and nfev < max_nfev:
+            p_S, _ = solve_trust_region_2d(B_S, g_S, Delta)
+            step_h = Sq @ p_S
+            Js = JS @ p_S
+            pred = -(0.5 * Js @ Js + step_h @ g_h)
+            x_new = x + d * step_h
+            f_new = fun_nocam(x_new, *args)
+            nfev += 1
+            shn = norm(step_h)
+            if not np.all(np.isfinite(f_new)):
+                Delta = 0.25 * shn
+                continue
+            cost_new = 0.5 * f_new @ f_new
+            actual = cost - cost_new
+            Delta_new, ratio = update_tr_radius(Delta, actual, pred, shn, shn > 0.95 * Delta)
+            status = check_termination(actual, cost, norm(d * step_h), norm(x), ratio, ftol, xtol)
+            if status is not None:
+                break
+            Delta = Delta_new
+        if actual > 0:
+            x, cost = x_new, cost_new
+            f, Jp, V, gp = lin(x)
+            njev += 1
+            g = gp.ravel()
+            scale_inv = np.maximum(np.sqrt(np.einsum("paa->pa", V)).ravel(), scale_inv)
+    return OptimizeResult(x=x, cost=cost, fun=f, grad=g, optimality=g_norm, nfev=nfev, njev=njev,
+                          status=status or 0, trace=trace)
+
+
 def rmse_px(res_vec):
     """sqrt(mean(|r_i|^2)) over observations, r_i the 2-vector pixel residual."""
     r = np.asarray(res_vec).reshape(-1, 2)

@@ -177,7 +177,25 @@ def golden_ba(name, rig, npts, variant, p_vis=1.0):
           "nfev", rt.nfev)
 
 
+def golden_nocam():
+    """PySBA.bundleAdjust_nocam (points only, pySBA.py:237-250) on an 8-camera rig."""
+    pb = make_rig("ring8", 600, seed=9, variant="volume", p_vis=0.8)
+    sba = PySBA(pb["cams_gt"].copy(), pb["pts0"].copy(), pb["points_2d"], pb["camera_ind"],
+                pb["point_ind"])
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        res = sba.bundleAdjust_nocam(1e-7)
+    np.savez_compressed(os.path.join(HERE, "ba_nocam_ring8_600.npz"), ref_x=res.x,
+                        ref_cost=res.cost, ref_nfev=res.nfev, ref_status=res.status,
+                        ref_log=buf.getvalue(), cams=pb["cams_gt"], **inputs_of(pb), **VERS)
+    print("ba_nocam_ring8_600: cost", res.cost, "nfev", res.nfev, "status", res.status)
+
+
 if __name__ == "__main__":
+    if "--only-nocam" in sys.argv:
+        golden_nocam()
+        sys.exit(0)
+    golden_nocam()
     golden_model()
     golden_example_cams()
     golden_ba("ba_ring4_planar2000", "ring4", 2000, "planar")

@@ -316,6 +316,26 @@ def test_unsorted_input_gives_same_solution(PySBA):
     np.testing.assert_allclose(perm_cost, rb.cost, rtol=1e-12)
 
 
+def test_bundleAdjust_nocam_points_only(PySBA, golden):
+    """PySBA.bundleAdjust_nocam (pySBA.py:237-250) — cameras fixed."""
+    g = golden("ba_nocam_ring8_600")
+    ora = O.trf_exact_nocam(g["cams"], g["pts0"], g["points_2d"], g["camera_ind"], g["point_ind"],
+                            ftol=1e-7)
+    sba = PySBA(g["cams"].copy(), g["pts0"].copy(), g["points_2d"], g["camera_ind"], g["point_ind"])
+    cams_before = sba.cameraArray.copy()
+    res = sba.bundleAdjust_nocam(1e-7)
+    assert res.x.shape == (3 * g["pts0"].shape[0],) and sba.points3D.shape == g["pts0"].shape
+    np.testing.assert_array_equal(sba.cameraArray, cams_before)            # cameras untouched
+    assert res.nfev == ora.nfev and res.status == ora.status
+    np.testing.assert_allclose(res.cost, ora.cost, rtol=1e-11)
+    np.testing.assert_allclose(res.x, ora.x, rtol=0, atol=1e-7)
+    # against the reference's own run (scipy, inexact LSMR): same optimum
+    np.testing.assert_allclose(res.cost, float(g["ref_cost"]), rtol=1e-9)
+    np.testing.assert_allclose(res.x, g["ref_x"], rtol=0, atol=1e-4)       # mm
+    np.testing.assert_allclose(res.cost, 0.5 * res.fun @ res.fun, rtol=1e-12)
+    assert res.grad.shape == res.x.shape
+
+
 # ----------------------------------------------------------------------------- error paths
 def test_error_behaviour(PySBA, Engine):
     from lasercalib_b200._cabi import LcbaError
@@ -339,7 +359,7 @@ def test_error_behaviour(PySBA, Engine):
     with pytest.raises(LcbaError, match="64 cameras"):
         eng.set_problem(np.zeros((65, 11)), pb["pts0"], pb["points_2d"], pb["camera_ind"], pb["point_ind"])
     with pytest.raises(NotImplementedError):
-        sba.bundleAdjust_nocam()
+        sba.bundleAdjust_sharedcam()
     eng.close()
 
 
