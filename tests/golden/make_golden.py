@@ -191,7 +191,32 @@ def golden_nocam():
     print("ba_nocam_ring8_600: cost", res.cost, "nfev", res.nfev, "status", res.status)
 
 
+def golden_io():
+    """Export / init formats of lasercalib/convert_params.py on the 17 example cameras."""
+    import cv2
+    np.NaN = np.nan            # the reference still uses np.NaN (removed in numpy 2)
+    from lasercalib.convert_params import readable_to_red_format, sba_to_readable_format
+    g = np.load(os.path.join(HERE, "model_example17.npz"))
+    cams = g["cams"]
+    readable = [sba_to_readable_format(c) for c in cams]
+    red = readable_to_red_format(readable)
+    raw = []
+    for n in [str(x) for x in g["cam_names"]]:
+        fs = cv2.FileStorage("/root/reference/example/calib_init_2024_05_02/%s.yaml" % n,
+                             cv2.FILE_STORAGE_READ)
+        raw.append((fs.getNode("camera_matrix").mat(), fs.getNode("distortion_coefficients").mat(),
+                    fs.getNode("rc_ext").mat(), fs.getNode("tc_ext").mat()))
+    np.savez_compressed(os.path.join(HERE, "io_example17.npz"), cams=cams,
+                        K=np.array([r["K"] for r in readable]), R=np.array([r["R"] for r in readable]),
+                        red=red, camera_matrix=np.array([r[0] for r in raw]),
+                        distortion=np.array([r[1] for r in raw]), rc_ext=np.array([r[2] for r in raw]),
+                        tc_ext=np.array([r[3] for r in raw]), **VERS)
+
+
 if __name__ == "__main__":
+    if "--only-io" in sys.argv:
+        golden_io()
+        sys.exit(0)
     if "--only-nocam" in sys.argv:
         golden_nocam()
         sys.exit(0)
@@ -201,3 +226,4 @@ if __name__ == "__main__":
     golden_ba("ba_ring4_planar2000", "ring4", 2000, "planar")
     golden_ba("ba_ring8_volume1500", "ring8", 1500, "volume")
     golden_ba("ba_example18_vis60_800", "example18", 800, "volume", p_vis=0.6)
+    golden_io()
