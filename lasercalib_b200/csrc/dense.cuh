@@ -20,23 +20,26 @@ k_chol_panel(double* __restrict__ A, int n, int k, int* __restrict__ fail) {
     D[i][j] = (i < nb && j < nb && j <= i) ? A[(size_t)(k + i) * n + k + j] : (i == j ? 1.0 : 0.0);
   }
   __syncthreads();
-  if (t < 32) {
+  // right-looking factorisation of the 32x32 diagonal block with the whole CTA:
+  // thread (ty, tx) of an 8x32 grid updates rows ty, ty+8, ... of column tx
+  {
+    const int tx = t & 31, ty = t >> 5;
     for (int j = 0; j < nb; ++j) {
       double d = D[j][j];
       if (!(d > 0.0)) { if (t == 0) atomicOr(fail, 1); d = 1.0; }
       d = sqrt(d);
-      __syncwarp();
+      __syncthreads();
       if (t == j) D[j][j] = d;
       if (t > j && t < nb) D[t][j] /= d;
-      __syncwarp();
-      if (t > j && t < nb) {
-        const double l = D[t][j];
-        for (int c = j + 1; c <= t; ++c) D[t][c] -= l * D[c][j];
+      __syncthreads();
+      if (tx > j && tx < nb) {
+        const double lc = D[tx][j];
+        for (int r = ty; r < nb; r += 8)
+          if (r >= tx) D[r][tx] -= D[r][j] * lc;
       }
-      __syncwarp();
+      __syncthreads();
     }
   }
-  __syncthreads();
   for (int e = t; e < nb * nb; e += blockDim.x) {
     const int i = e / nb, j = e % nb;
     if (j <= i) A[(size_t)(k + i) * n + k + j] = D[i][j];

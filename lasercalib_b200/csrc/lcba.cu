@@ -77,7 +77,7 @@ struct lcba_handle {
   int32_t* d_pt = nullptr;
   int32_t* d_perm = nullptr;
   uint32_t* d_obs_start = nullptr;
-  int32_t* d_bin_p0 = nullptr;
+  BinEntry* d_bins = nullptr;
   unsigned long long* d_mask = nullptr;
   // solver state
   double *d_Vg = nullptr, *d_scl_p = nullptr, *d_gt_p = nullptr, *d_Lz = nullptr, *d_gn_p = nullptr;
@@ -376,8 +376,8 @@ extern "C" int lcba_set_problem(lcba_t* h, int32_t C, int64_t P, int64_t N, cons
   h->B = LIN_THREADS - h->kmax;
   if (h->B < 32) { set_error(h, "lcba_set_problem: too many observations per point"); return LCBA_E_UNSUPPORTED; }
   h->nbins = N / h->B + 1;
-  LCBA_TRY(dev_alloc(h, &h->d_bin_p0, (size_t)h->nbins + 1));
-  k_bin_table<<<nblk(h->nbins + 1, 256), 256, 0, st>>>(h->d_obs_start, P, h->nbins, h->B, h->d_bin_p0);
+  LCBA_TRY(dev_alloc(h, &h->d_bins, (size_t)h->nbins + 2));
+  k_bin_table<<<nblk(h->nbins + 1, 256), 256, 0, st>>>(h->d_obs_start, P, h->nbins, h->B, h->d_bins);
   h->launches++;
 
   // solver buffers
@@ -587,7 +587,7 @@ static int pass_linearize(lcba_t* h, int first) {
   LCBA_TRY(build_tables(h, w));
   const size_t smem = linearize_smem_doubles(C) * 8;
   KL(h, "linearize", k_linearize<<<h->lin_grid, LIN_THREADS, smem, h->stream>>>(
-        h->d_tab[w], h->d_pts[w], h->d_uv, h->d_cam, h->d_pt, h->d_w, h->d_obs_start, h->d_bin_p0,
+        h->d_tab[w], h->d_pts[w], h->d_uv, h->d_cam, h->d_pt, h->d_w, h->d_obs_start, h->d_bins,
         h->nbins, C, h->d_Vg, h->d_campart, h->d_part));
   KL(h, "reduce", k_reduce_cols<<<nblk(C * CAMSUM, 128), 128, 0, h->stream>>>(
         h->d_campart, h->lin_grid, C * CAMSUM, h->d_camsum));
@@ -734,7 +734,7 @@ static int pass_backsub(lcba_t* h) {
   const int C = h->C, w = h->cur;
   const size_t smem = ((size_t)C * CAMTAB + 2 * (size_t)C * NCP + 2 * LIN_THREADS * 3) * 8;
   KL(h, "backsub", k_backsub<<<h->lin_grid, LIN_THREADS, smem, h->stream>>>(
-        h->d_tab[w], h->d_pts[w], h->d_cam, h->d_pt, h->d_w, h->d_obs_start, h->d_bin_p0, h->nbins, C,
+        h->d_tab[w], h->d_pts[w], h->d_cam, h->d_pt, h->d_w, h->d_obs_start, h->d_bins, h->nbins, C,
         h->d_Vg, h->d_Lz, h->d_scl_p, h->d_gt_c, h->d_gt_p, h->d_pc, h->d_gn_p, h->d_part));
   KL(h, "reduce", k_reduce_scalars<<<BS_K, 256, 0, h->stream>>>(h->d_part, h->lin_grid, BS_K, h->d_red, BS_K));
   LCBA_TRY(allreduce(h, h->d_red, BS_K, NCCL_SUM));

@@ -18,31 +18,38 @@ constexpr int LIN_WARPS = LIN_THREADS / 32;
 constexpr int CAMSUM = 22;          // per camera: g_c (11) then diag(J^T J) (11)
 constexpr int CTAB_LD = 23;         // odd row stride of the warp-private camera tables
 
-struct BinRange { long long p0, p1; long long o0; int nobs; };
-
 // Bin b owns the points whose first observation index lies in [b*B, (b+1)*B); the first
-// point of every bin is precomputed once at ingest (k_bin_table), so a CTA finds its work
-// with two dependent loads instead of two binary searches.
+// point and first observation of every bin are precomputed at ingest (k_bin_table): every
+// thread reads its bin's range with two uniform 8-byte loads, and the NEXT bin's range is
+// prefetched while the current one is processed (no thread-0 lookup + barrier).
+struct BinEntry { int32_t p0; uint32_t o0; };
+
 __global__ void k_bin_table(const uint32_t* __restrict__ obs_start, long long P, long long nbins,
-                            int B, int32_t* __restrict__ bin_p0) {
+                            int B, BinEntry* __restrict__ bins) {
   const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (b > nbins) return;
-  bin_p0[b] = (b == nbins) ? (int32_t)P
-                           : (int32_t)lower_bound_u32(obs_start, P, (unsigned long long)b * B);
+  const long long p0 = (b == nbins) ? P : lower_bound_u32(obs_start, P, (unsigned long long)b * B);
+  bins[b].p0 = (int32_t)p0;
+  bins[b].o0 = obs_start[p0];
 }
 
-__device__ __forceinline__ void bin_range(const uint32_t* __restrict__ obs_start,
-                                          const int32_t* __restrict__ bin_p0, long long bin,
-                                          BinRange* s_bin) {
-  if (threadIdx.x == 0) {
-    const long long p0 = bin_p0[bin], p1 = bin_p0[bin + 1];
-    const uint32_t a = obs_start[p0], b = obs_start[p1];
-    s_bin->p0 = p0;
-    s_bin->p1 = p1;
-    s_bin->o0 = a;
-    s_bin->nobs = (int)(b - a);
+struct BinRange { long long p0, p1; long long o0; int nobs; };
+
+__device__ __forceinline__ BinRange load_bin(const BinEntry* __restrict__ bins, long long bin,
+                                             long long nbins) {
+  BinRange r;
+  if (bin < nbins) {
+    const int2 e0 = *reinterpret_cast<const int2*>(bins + bin);
+    const int2 e1 = *reinterpret_cast<const int2*>(bins + bin + 1);
+    r.p0 = e0.x;
+    r.o0 = (unsigned)e0.y;
+    r.p1 = e1.x;
+    r.nobs = (int)((unsigned)e1.y - (unsigned)e0.y);
+  } else {
+    r.p0 = r.p1 = r.o0 = 0;
+    r.nobs = 0;
   }
-  __syncthreads();
+  return r;
 }
 
 // dynamic smem layout (doubles): tab[C*CAMTAB | even] pv[256*9] ctab[8*C*23]
@@ -52,11 +59,11 @@ __host__ __device__ inline size_t linearize_smem_doubles(int C) {
 
 // Vg[p][0..5] = V (00,01,02,11,12,22), Vg[p][6..8] = g_p.
 // cam_part[block][C*22], cost_part[block]
-__global__ void __launch_bounds__(LIN_THREADS)
+__global__ void __launch_bounds__(LIN_THREADS, 3)
 k_linearize(const double* __restrict__ tab, const double* __restrict__ pts,
             const double2* __restrict__ uv, const uint8_t* __restrict__ cam,
             const int32_t* __restrict__ pt, const double* __restrict__ wgt,
-            const uint32_t* __restrict__ obs_start, const int32_t* __restrict__ bin_p0,
+            const uint32_t* __restrict__ obs_start, const BinEntry* __restrict__ bins,
             long long nbins, int C, double* __restrict__ Vg, double* __restrict__ cam_part,
             double* __restrict__ cost_part) {
   extern __shared__ double s_dyn[];
@@ -64,19 +71,21 @@ k_linearize(const double* __restrict__ tab, const double* __restrict__ pts,
   double* s_pv = s_dyn + ((C * CAMTAB + 1) & ~1);
   double* s_ctab = s_pv + LIN_THREADS * 9;
   __shared__ double s_red[32];
-  __shared__ BinRange s_bin;
 
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
   load_tables_smem(tab, s_tab, C);
   for (int i = t; i < LIN_WARPS * C * CTAB_LD; i += LIN_THREADS) s_ctab[i] = 0.0;
   double cost = 0.0;
   double* my_ctab = s_ctab + (size_t)wid * C * CTAB_LD;
+  BinRange nxt = load_bin(bins, blockIdx.x, nbins);
+  __syncthreads();
 
   for (long long bin = blockIdx.x; bin < nbins; bin += gridDim.x) {
-    bin_range(obs_start, bin_p0, bin, &s_bin);   // contains __syncthreads (also orders smem reuse)
-    const long long p0 = s_bin.p0, o0 = s_bin.o0;
-    const long long npts = s_bin.p1 - p0;
-    const int nobs = s_bin.nobs;
+    const BinRange cur = nxt;
+    nxt = load_bin(bins, bin + gridDim.x, nbins);      // prefetch
+    const long long p0 = cur.p0, o0 = cur.o0;
+    const long long npts = cur.p1 - p0;
+    const int nobs = cur.nobs;
     uint8_t c8 = 255;
     double cv[CAMSUM];
     if (t < nobs) {
@@ -126,13 +135,21 @@ k_linearize(const double* __restrict__ tab, const double* __restrict__ pts,
     }
     __syncthreads();
     // per-point sums (fixed order => deterministic)
-    for (long long idx = t; idx < npts * 9; idx += LIN_THREADS) {
+    // two lanes per (point, value): even / odd observations, combined with one shuffle
+    for (long long base = 0; base < npts * 18; base += LIN_THREADS) {
+      const long long idx2 = base + t;
+      const bool act = idx2 < npts * 18;
+      const long long idx = (act ? idx2 : 0) >> 1;
+      const int half = (int)(idx2 & 1);
       const long long q = idx / 9;
       const int e = (int)(idx - q * 9);
-      const int f0 = (int)(obs_start[p0 + q] - o0), f1 = (int)(obs_start[p0 + q + 1] - o0);
       double s = 0.0;
-      for (int i = f0; i < f1; ++i) s += s_pv[i * 9 + e];
-      Vg[(p0 + q) * 9 + e] = s;
+      if (act) {
+        const int f0 = (int)(obs_start[p0 + q] - o0), f1 = (int)(obs_start[p0 + q + 1] - o0);
+        for (int i = f0 + half; i < f1; i += 2) s += s_pv[i * 9 + e];
+      }
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      if (act && half == 0) Vg[(p0 + q) * 9 + e] = s;
     }
     __syncthreads();
   }
@@ -294,7 +311,7 @@ __global__ void __launch_bounds__(LIN_THREADS, 3)
 k_backsub(const double* __restrict__ tab, const double* __restrict__ pts,
           const uint8_t* __restrict__ cam, const int32_t* __restrict__ pt,
           const double* __restrict__ wgt, const uint32_t* __restrict__ obs_start,
-          const int32_t* __restrict__ bin_p0, long long nbins, int C,
+          const BinEntry* __restrict__ bins, long long nbins, int C,
           const double* __restrict__ Vg,
           const double* __restrict__ Lz, const double* __restrict__ scl,
           const double* __restrict__ gt_c, const double* __restrict__ gt_p,
@@ -307,7 +324,6 @@ k_backsub(const double* __restrict__ tab, const double* __restrict__ pts,
   double* s_tv = s_pc + C * NCP;          // [256][3]
   double* s_pp = s_tv + LIN_THREADS * 3;  // [256][3], slot = first local observation of the point
   __shared__ double s_red[32];
-  __shared__ BinRange s_bin;
   const int t = threadIdx.x;
   load_tables_smem(tab, s_tab, C);
   for (int i = t; i < C * NCP; i += LIN_THREADS) { s_gc[i] = gt_c[i]; s_pc[i] = pc[i]; }
@@ -315,11 +331,14 @@ k_backsub(const double* __restrict__ tab, const double* __restrict__ pts,
 #pragma unroll
   for (int k = 0; k < BS_K; ++k) acc[k] = 0.0;
 
+  BinRange nxt = load_bin(bins, blockIdx.x, nbins);
+  __syncthreads();
   for (long long bin = blockIdx.x; bin < nbins; bin += gridDim.x) {
-    bin_range(obs_start, bin_p0, bin, &s_bin);
-    const long long p0 = s_bin.p0, o0 = s_bin.o0;
-    const long long npts = s_bin.p1 - p0;
-    const int nobs = s_bin.nobs;
+    const BinRange cur = nxt;
+    nxt = load_bin(bins, bin + gridDim.x, nbins);      // prefetch
+    const long long p0 = cur.p0, o0 = cur.o0;
+    const long long npts = cur.p1 - p0;
+    const int nobs = cur.nobs;
     double jp[2][3];
     double A0 = 0, A1 = 0, b0 = 0, b1 = 0;
     int q_of = 0;

@@ -7,30 +7,29 @@
 namespace lcba {
 
 constexpr int NCP = 11;       // rotvec(3) t(3) f k1 k2 cx cy  (pySBA.py:31-35)
-// Per-camera table: [0..10] parameters, [11..19] R row-major, [20..46] dR/dr_k (k-major,
-// each 3x3 row-major).  Stride 49 doubles (odd) => conflict-free shared-memory reads
-// when the lanes of a half-warp address different cameras.
+// Per-camera table: [0..10] parameters, [11..19] R row-major, [20..28] right Jacobian J_r of
+// SO(3) row-major:  d(R X)/dr = -R [X]x J_r.  Stride 29 doubles (odd) => conflict-free
+// shared-memory reads when the lanes of a half-warp address different cameras; the table is
+// read once per observation by every streaming pass, so it is kept small (shared-memory
+// bandwidth, not FP64, was the limiter with the 27 doubles of explicit dR/dr_k).
 constexpr int CT_R = 11;
-constexpr int CT_DR = 20;
-constexpr int CAMTAB = 49;
+constexpr int CT_JR = 20;
+constexpr int CAMTAB = 29;
 
-// R(r) = I + a K + b K^2 and dR/dr_k = c1 r_k K + a E_k + c2 r_k K^2 + b (E_k K + K E_k),
-// a = sin t / t, b = (1 - cos t)/t^2, c1 = (t cos t - sin t)/t^3, c2 = (t sin t - 2(1-cos t))/t^4,
-// Taylor series below t = 0.1 (t = 0 => identity, like pySBA.py:66-68).
-__device__ __forceinline__ void rodrigues_coeffs(double t2, double& a, double& b, double& c1,
-                                                 double& c2) {
+// R(r) = I + a K + b K^2,  J_r(r) = I - b K + c K^2,  K = [r]x,
+// a = sin t / t, b = (1 - cos t)/t^2, c = (t - sin t)/t^3; Taylor series below t = 0.1
+// (t = 0 => identity, like pySBA.py:66-68).
+__device__ __forceinline__ void rodrigues_coeffs(double t2, double& a, double& b, double& c) {
   if (t2 < 0.01) {
     a = 1.0 - t2 / 6.0 * (1.0 - t2 / 20.0 * (1.0 - t2 / 42.0 * (1.0 - t2 / 72.0 * (1.0 - t2 / 110.0))));
     b = 0.5 * (1.0 - t2 / 12.0 * (1.0 - t2 / 30.0 * (1.0 - t2 / 56.0 * (1.0 - t2 / 90.0 * (1.0 - t2 / 132.0)))));
-    c1 = -1.0 / 3.0 + t2 * (1.0 / 30.0 + t2 * (-1.0 / 840.0 + t2 * (1.0 / 45360.0 + t2 * (-1.0 / 3991680.0 + t2 / 518918400.0))));
-    c2 = -1.0 / 12.0 + t2 * (1.0 / 180.0 + t2 * (-1.0 / 6720.0 + t2 * (1.0 / 453600.0 + t2 * (-1.0 / 47900160.0 + t2 / 7264857600.0))));
+    c = 1.0 / 6.0 * (1.0 - t2 / 20.0 * (1.0 - t2 / 42.0 * (1.0 - t2 / 72.0 * (1.0 - t2 / 110.0 * (1.0 - t2 / 156.0)))));
   } else {
-    double t = sqrt(t2), s, c;
-    sincos(t, &s, &c);
-    a = s / t;
-    b = (1.0 - c) / t2;
-    c1 = (t * c - s) / (t * t2);
-    c2 = (t * s - 2.0 * (1.0 - c)) / (t2 * t2);
+    double t = sqrt(t2), sn, cs;
+    sincos(t, &sn, &cs);
+    a = sn / t;
+    b = (1.0 - cs) / t2;
+    c = (t - sn) / (t * t2);
   }
 }
 
@@ -39,33 +38,18 @@ __device__ inline void cam_table_build(const double* __restrict__ cam, double* _
   for (int i = 0; i < NCP; ++i) T[i] = cam[i];
   const double r0 = cam[0], r1 = cam[1], r2 = cam[2];
   const double t2 = r0 * r0 + r1 * r1 + r2 * r2;
-  double a, b, c1, c2;
-  rodrigues_coeffs(t2, a, b, c1, c2);
+  double a, b, c;
+  rodrigues_coeffs(t2, a, b, c);
   double K[9] = {0, -r2, r1, r2, 0, -r0, -r1, r0, 0};
   double K2[9];
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 3; ++j)
       K2[3 * i + j] = K[3 * i] * K[j] + K[3 * i + 1] * K[3 + j] + K[3 * i + 2] * K[6 + j];
-  for (int i = 0; i < 9; ++i) T[CT_R + i] = ((i % 4 == 0) ? 1.0 : 0.0) + a * K[i] + b * K2[i];
-  const double rv[3] = {r0, r1, r2};
-  for (int k = 0; k < 3; ++k) {
-    double E[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    const int i = (k + 1) % 3, j = (k + 2) % 3;
-    E[3 * j + i] = 1.0;
-    E[3 * i + j] = -1.0;
-    for (int p = 0; p < 3; ++p)
-      for (int q = 0; q < 3; ++q) {
-        double ek = 0, ke = 0;
-        for (int m = 0; m < 3; ++m) {
-          ek += E[3 * p + m] * K[3 * m + q];
-          ke += K[3 * p + m] * E[3 * m + q];
-        }
-        T[CT_DR + 9 * k + 3 * p + q] =
-            c1 * rv[k] * K[3 * p + q] + a * E[3 * p + q] + c2 * rv[k] * K2[3 * p + q] + b * (ek + ke);
-      }
+  for (int i = 0; i < 9; ++i) {
+    const double eye = (i % 4 == 0) ? 1.0 : 0.0;
+    T[CT_R + i] = eye + a * K[i] + b * K2[i];
+    T[CT_JR + i] = eye - b * K[i] + c * K2[i];
   }
-  T[47] = 0.0;
-  T[48] = 0.0;
 }
 
 // Residual and Jacobian blocks of one observation.
@@ -119,14 +103,20 @@ __device__ __forceinline__ void obs_linearize(const double* __restrict__ T, doub
   // G = w * d(u,v)/dXc
   const double g00 = e00 * iz, g01 = e01 * iz, g02 = -(e00 * x + e01 * y) * iz;
   const double g10 = e01 * iz, g11 = e11 * iz, g12 = -(e01 * x + e11 * y) * iz;
+  // d(u,v)/dr_k = G * (-R (X x J_r[:,k]));  GR = G R is needed for Jp anyway
+  double GR[2][3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    GR[0][j] = fma(g00, R[j], fma(g01, R[3 + j], g02 * R[6 + j]));
+    GR[1][j] = fma(g10, R[j], fma(g11, R[3 + j], g12 * R[6 + j]));
+  }
+  const double* Jr = T + CT_JR;
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    const double* D = T + CT_DR + 9 * k;
-    const double a0 = fma(D[0], X, fma(D[1], Y, D[2] * Z));
-    const double a1 = fma(D[3], X, fma(D[4], Y, D[5] * Z));
-    const double a2 = fma(D[6], X, fma(D[7], Y, D[8] * Z));
-    o.Jc[0][k] = fma(g00, a0, fma(g01, a1, g02 * a2));
-    o.Jc[1][k] = fma(g10, a0, fma(g11, a1, g12 * a2));
+    const double c0 = Jr[k], c1 = Jr[3 + k], c2 = Jr[6 + k];
+    const double m0 = fma(Y, c2, -Z * c1), m1 = fma(Z, c0, -X * c2), m2 = fma(X, c1, -Y * c0);
+    o.Jc[0][k] = -fma(GR[0][0], m0, fma(GR[0][1], m1, GR[0][2] * m2));
+    o.Jc[1][k] = -fma(GR[1][0], m0, fma(GR[1][1], m1, GR[1][2] * m2));
   }
   o.Jc[0][3] = g00; o.Jc[0][4] = g01; o.Jc[0][5] = g02;
   o.Jc[1][3] = g10; o.Jc[1][4] = g11; o.Jc[1][5] = g12;
@@ -136,8 +126,8 @@ __device__ __forceinline__ void obs_linearize(const double* __restrict__ T, doub
   o.Jc[0][8] = wfn2 * x; o.Jc[1][8] = wfn2 * y;
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
-    o.Jp[0][j] = fma(g00, R[j], fma(g01, R[3 + j], g02 * R[6 + j]));
-    o.Jp[1][j] = fma(g10, R[j], fma(g11, R[3 + j], g12 * R[6 + j]));
+    o.Jp[0][j] = GR[0][j];
+    o.Jp[1][j] = GR[1][j];
   }
 }
 
