@@ -178,6 +178,8 @@ int lcba_time_device(lcba_t* h, int32_t what, int32_t reps, double* ms_out);
  * NCCL inside lcba_solve / lcba_linearize.  The unique id is created on rank 0 and
  * distributed by the host (torch.distributed broadcast). */
 int lcba_nccl_unique_id(void* id_out128);
+/* id128 != NULL: create the process-wide communicator (collective over all ranks);
+ * id128 == NULL: attach the communicator this process created earlier to another handle. */
 int lcba_comm_init(lcba_t* h, int32_t rank, int32_t nranks, const void* id128);
 /* total point count over all ranks is needed for max_nfev = 100*n and is all-reduced. */
 

@@ -264,8 +264,9 @@ class Engine:
             raise LcbaError(rc, lib.lcba_last_error(None).decode())
         return buf.raw
 
-    def comm_init(self, rank, nranks, unique_id):
-        buf = C.create_string_buffer(bytes(unique_id), 128)
+    def comm_init(self, rank, nranks, unique_id=None):
+        """unique_id bytes: create the process-wide communicator; None: attach the existing one."""
+        buf = None if unique_id is None else C.create_string_buffer(bytes(unique_id), 128)
         self._check(self.lib.lcba_comm_init(self.h, int(rank), int(nranks), buf))
 
 

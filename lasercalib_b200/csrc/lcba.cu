@@ -107,6 +107,10 @@ struct lcba_handle {
 };
 
 static std::string g_last_error;
+// One NCCL communicator per process (one process per GPU): created by the first
+// lcba_comm_init that carries a unique id, attached by later handles (id == NULL).
+static ncclComm_t g_comm = nullptr;
+static int g_comm_rank = -1, g_comm_nranks = 0, g_comm_device = -1;
 static void set_error(lcba_t* h, const std::string& s) {
   if (h) h->err = s;
   g_last_error = s;
@@ -245,7 +249,7 @@ extern "C" int lcba_create(lcba_t** out, int device) {
 extern "C" void lcba_destroy(lcba_t* h) {
   if (!h) return;
   cudaSetDevice(h->device);
-  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  h->comm = nullptr;   // the communicator belongs to the process (see g_comm)
   dev_free_all(h);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
@@ -387,7 +391,7 @@ extern "C" int lcba_set_problem(lcba_t* h, int32_t C, int64_t P, int64_t N, cons
   LCBA_TRY(dev_alloc(h, &h->d_gt_p, (size_t)P * 3));
   LCBA_TRY(dev_alloc(h, &h->d_Lz, (size_t)P * 9));
   LCBA_TRY(dev_alloc(h, &h->d_gn_p, (size_t)P * 3));
-  LCBA_TRY(dev_alloc(h, &h->d_camsum, (size_t)C * CAMSUM + 1));
+  LCBA_TRY(dev_alloc(h, &h->d_camsum, (size_t)C * CAMSUM + 1 + PP_K));
   LCBA_TRY(dev_alloc(h, &h->d_scl_c, (size_t)n));
   LCBA_TRY(dev_alloc(h, &h->d_gt_c, (size_t)n));
   LCBA_TRY(dev_alloc(h, &h->d_g_c, (size_t)n));
@@ -593,15 +597,17 @@ static int pass_linearize(lcba_t* h, int first) {
         h->d_campart, h->lin_grid, C * CAMSUM, h->d_camsum));
   KL(h, "reduce", k_reduce_scalars<<<1, 256, 0, h->stream>>>(h->d_part, h->lin_grid, 1,
                                                              h->d_camsum + C * CAMSUM, 1));
-  LCBA_TRY(allreduce(h, h->d_camsum, (size_t)C * CAMSUM + 1, NCCL_SUM));
-  KL(h, "ctl", k_ctl_lin<<<1, 256, 0, h->stream>>>(h->d_camsum, h->d_cams[w], h->d_scl_c, h->d_gt_c,
-                                                   h->d_g_c, C, h->d_ctl, first, h->fix_cameras));
+  // per-point scaling does not depend on the camera sums: run it first so that ONE sum
+  // all-reduce carries [camera sums | cost | point sums] and one max all-reduce |g|_inf
+  double* pp = h->d_camsum + C * CAMSUM + 1;
   KL(h, "point_prep", k_point_prep<<<h->pt_grid, 256, 0, h->stream>>>(
         h->d_Vg, h->d_pts[w], h->d_scl_p, h->d_gt_p, h->P, first, h->d_part));
-  KL(h, "reduce", k_reduce_scalars<<<PP_K, 256, 0, h->stream>>>(h->d_part, h->pt_grid, PP_K, h->d_red, 3));
-  LCBA_TRY(allreduce(h, h->d_red, 3, NCCL_SUM));
-  LCBA_TRY(allreduce(h, h->d_red + 3, 1, NCCL_MAX));
-  KL(h, "ctl", k_ctl_lin2<<<1, 1, 0, h->stream>>>(h->d_red, h->d_ctl, first));
+  KL(h, "reduce", k_reduce_scalars<<<PP_K, 256, 0, h->stream>>>(h->d_part, h->pt_grid, PP_K, pp, 3));
+  LCBA_TRY(allreduce(h, h->d_camsum, (size_t)C * CAMSUM + 1 + 3, NCCL_SUM));
+  LCBA_TRY(allreduce(h, pp + 3, 1, NCCL_MAX));
+  KL(h, "ctl", k_ctl_lin<<<1, 256, 0, h->stream>>>(h->d_camsum, h->d_cams[w], h->d_scl_c, h->d_gt_c,
+                                                   h->d_g_c, C, h->d_ctl, first, h->fix_cameras));
+  KL(h, "ctl", k_ctl_lin2<<<1, 1, 0, h->stream>>>(pp, h->d_ctl, first));
   return check_launch(h, "linearize pass");
 }
 
@@ -819,11 +825,26 @@ extern "C" int lcba_solve(lcba_t* h, const lcba_options* opt_in, lcba_result* re
   double cost = h->h_ctl->cost, g_norm = h->h_ctl->g_norm;
   double step_norm = NAN, actual = NAN;
   double last_reg = 0.0;
+  // After an accepted step the re-linearisation is only enqueued; its scalars (cost, |g|_inf)
+  // come back with the NEXT trial's status in one host sync per iteration.  If they say
+  // "gtol reached", the speculatively evaluated trial is simply discarded.
+  bool lin_pending = false;
+  auto absorb_lin = [&]() {
+    cost = h->h_ctl->cost;
+    g_norm = h->h_ctl->g_norm;
+    lin_pending = false;
+  };
   while (true) {
-    if (g_norm < opt.gtol) status = LCBA_STATUS_GTOL;
-    add_trace(h, iteration, nfev, cost, actual, step_norm, g_norm, h->h_ctl->Delta, last_reg);
-    if (status >= 0 || nfev >= max_nfev) break;
-    if (opt.max_iterations > 0 && iteration >= opt.max_iterations) break;
+    const bool limits = nfev >= max_nfev || (opt.max_iterations > 0 && iteration >= opt.max_iterations);
+    if (lin_pending && (status >= 0 || limits)) {
+      LCBA_TRY(read_ctl(h));
+      absorb_lin();
+    }
+    if (!lin_pending) {
+      if (g_norm < opt.gtol) status = LCBA_STATUS_GTOL;
+      add_trace(h, iteration, nfev, cost, actual, step_norm, g_norm, h->h_ctl->Delta, last_reg);
+      if (status >= 0 || limits) break;
+    }
 
     LCBA_TRY(pass_jdot(h));
     if (h->fix_cameras) {
@@ -837,13 +858,21 @@ extern "C" int lcba_solve(lcba_t* h, const lcba_options* opt_in, lcba_result* re
     }
     double mu = 0.0;
     bool have_trial = false;
+    double prev_actual = actual, prev_step = step_norm;
     actual = -1.0;
     int term = -1;
+    bool gtol_hit = false;
     while (true) {   // Cholesky retry loop (extra camera damping on breakdown)
       if (!h->fix_cameras) LCBA_TRY(pass_camera_solve(h, mu));
       LCBA_TRY(pass_backsub(h));
       LCBA_TRY(pass_trial(h));
       LCBA_TRY(read_ctl(h));
+      if (lin_pending) {
+        absorb_lin();
+        if (g_norm < opt.gtol) status = LCBA_STATUS_GTOL;
+        add_trace(h, iteration, nfev, cost, prev_actual, prev_step, g_norm, h->h_ctl->Delta, last_reg);
+        if (status >= 0) { gtol_hit = true; break; }
+      }
       if (h->h_ctl->retry) {
         mu = std::max(std::max(10.0 * mu, 10.0 * h->h_ctl->reg_term), 1e-13);
         if (mu > 1e6) {
@@ -856,6 +885,7 @@ extern "C" int lcba_solve(lcba_t* h, const lcba_options* opt_in, lcba_result* re
       have_trial = true;
       break;
     }
+    if (gtol_hit) { actual = prev_actual; step_norm = prev_step; break; }
     last_reg = h->h_ctl->reg_term;
     // inner loop: trials until the cost decreases (trf.py:503-541); scipy would spin up to
     // max_nfev = 100 n when all tolerances are 0 and the step underflows — cap the rejections
@@ -882,9 +912,7 @@ extern "C" int lcba_solve(lcba_t* h, const lcba_options* opt_in, lcba_result* re
       KL(h, "ctl", k_ctl_commit<<<1, 1, 0, h->stream>>>(h->d_ctl));
       LCBA_TRY(pass_linearize(h, 0));
       njev++;
-      LCBA_TRY(read_ctl(h));
-      cost = h->h_ctl->cost;
-      g_norm = h->h_ctl->g_norm;
+      lin_pending = true;
     } else {
       step_norm = 0.0;
       actual = 0.0;
@@ -1024,14 +1052,32 @@ extern "C" int lcba_nccl_unique_id(void* id_out128) {
 }
 
 extern "C" int lcba_comm_init(lcba_t* h, int32_t rank, int32_t nranks, const void* id128) {
-  if (!h || !id128 || nranks < 1 || rank < 0 || rank >= nranks) { set_error(h, "lcba_comm_init: bad argument"); return LCBA_E_ARG; }
+  if (!h || nranks < 1 || rank < 0 || rank >= nranks) { set_error(h, "lcba_comm_init: bad argument"); return LCBA_E_ARG; }
   std::string err;
   if (!nccl_load(err)) { set_error(h, err); return LCBA_E_NCCL; }
   cudaSetDevice(h->device);
+  if (!id128) {
+    // attach the communicator this process already created
+    if (!g_comm || g_comm_rank != rank || g_comm_nranks != nranks || g_comm_device != h->device) {
+      set_error(h, "lcba_comm_init: no matching process communicator to attach (pass a unique id first)");
+      return LCBA_E_STATE;
+    }
+    h->comm = g_comm;
+    h->rank = rank;
+    h->nranks = nranks;
+    return LCBA_OK;
+  }
   ncclUniqueId id;
   memcpy(&id, id128, sizeof(id));
-  int rc = g_nccl.CommInitRank(&h->comm, nranks, id, rank);
-  if (rc != 0) { set_error(h, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(rc)); h->comm = nullptr; return LCBA_E_NCCL; }
+  ncclComm_t comm = nullptr;
+  int rc = g_nccl.CommInitRank(&comm, nranks, id, rank);
+  if (rc != 0) { set_error(h, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(rc)); return LCBA_E_NCCL; }
+  if (g_comm) g_nccl.CommDestroy(g_comm);
+  g_comm = comm;
+  g_comm_rank = rank;
+  g_comm_nranks = nranks;
+  g_comm_device = h->device;
+  h->comm = comm;
   h->rank = rank;
   h->nranks = nranks;
   return LCBA_OK;

@@ -58,13 +58,47 @@ def shard_bounds(point_ind, n_points, nranks):
     return b
 
 
+_sorted_cache = {}     # (data pointer, size) -> bool, so repeated calls on the same array are O(1)
+
+
+def _is_point_major(point_ind):
+    key = (point_ind.ctypes.data, point_ind.size, point_ind.dtype.str)
+    hit = _sorted_cache.get(key)
+    if hit is None:
+        hit = bool(point_ind.size < 2 or np.all(point_ind[1:] >= point_ind[:-1]))
+        if len(_sorted_cache) > 64:
+            _sorted_cache.clear()
+        _sorted_cache[key] = hit
+    return hit
+
+
 def shard_problem(points3D, points2D, camera_ind, point_ind, weights, rank, nranks, bounds=None):
     """This rank's slice: points [lo, hi), the observations that reference them (local point
     indices), all cameras implied.  Returns dict(pts, points_2d, camera_ind, point_ind,
-    weights, lo, hi, obs_sel)."""
+    weights, lo, hi, obs_sel); obs_sel indexes the caller's observation arrays (a slice for
+    point-major input, an index array otherwise)."""
     point_ind = np.asarray(point_ind)
+    P = points3D.shape[0]
+    N = point_ind.size
+    if N > 1 and bounds is None and _is_point_major(point_ind):
+        # point-major input (the reference's order): shards are contiguous observation ranges,
+        # found by binary search; the observation arrays are sliced, not copied
+        b = np.zeros(nranks + 1, dtype=np.int64)
+        b[nranks] = P
+        for r in range(1, nranks):
+            b[r] = int(point_ind[min(N - 1, (N * r) // nranks)]) + (1 if N * r // nranks > 0 else 0)
+        b = np.minimum(np.maximum.accumulate(b), P)
+        lo, hi = int(b[rank]), int(b[rank + 1])
+        o0 = int(np.searchsorted(point_ind, lo, side="left"))
+        o1 = int(np.searchsorted(point_ind, hi, side="left"))
+        w = None if weights is None else np.asarray(weights).reshape(-1)[o0:o1]
+        return dict(pts=np.ascontiguousarray(points3D[lo:hi]),
+                    points_2d=np.asarray(points2D)[o0:o1],
+                    camera_ind=np.asarray(camera_ind)[o0:o1],
+                    point_ind=point_ind[o0:o1] - lo,
+                    weights=w, lo=lo, hi=hi, obs_sel=slice(o0, o1), bounds=b)
     if bounds is None:
-        bounds = shard_bounds(point_ind, points3D.shape[0], nranks)
+        bounds = shard_bounds(point_ind, P, nranks)
     lo, hi = int(bounds[rank]), int(bounds[rank + 1])
     sel = np.nonzero((point_ind >= lo) & (point_ind < hi))[0]
     w = None if weights is None else np.asarray(weights).reshape(-1)[sel]
@@ -75,16 +109,24 @@ def shard_problem(points3D, points2D, camera_ind, point_ind, weights, rank, nran
                 weights=w, lo=lo, hi=hi, obs_sel=sel, bounds=bounds)
 
 
+_process_comm = {}     # world size -> True once this process created its NCCL communicator
+
+
 def connect_engine(engine):
-    """Create the NCCL communicator of `engine` across the torch.distributed job."""
+    """Give `engine` the NCCL communicator of this process across the torch.distributed job
+    (created once per process, attached to every later engine)."""
     import torch.distributed as dist
     from . import _cabi
     rank, ws, _ = world()
     if ws == 1:
         return
+    if _process_comm.get(ws):
+        engine.comm_init(rank, ws, None)
+        return
     box = [_cabi.Engine.nccl_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(box, src=0)
     engine.comm_init(rank, ws, box[0])
+    _process_comm[ws] = True
 
 
 def allgather_rows(local, bounds):

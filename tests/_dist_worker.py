@@ -72,7 +72,7 @@ def main():
     D.allreduce_sum(cnt)
     assert np.all(cnt == 1)
     # balance: no rank holds more than 1.5x its fair share of observations (+ one point)
-    assert sh["obs_sel"].size <= 1.5 * pi.size / ws + C
+    assert sh["point_ind"].size <= 1.5 * pi.size / ws + C
     import torch.distributed as dist
     dist.barrier()
     dist.destroy_process_group()
