@@ -147,7 +147,7 @@ def main():
     ap.add_argument("--rig", default="ring24")
     ap.add_argument("--points", type=int, default=1_000_000)
     ap.add_argument("--pvis", type=float, default=1.0)
-    ap.add_argument("--cpu-points", type=int, default=3000)
+    ap.add_argument("--cpu-points", type=int, default=12000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     K, W = args.steps, max(args.warmup, 0)
