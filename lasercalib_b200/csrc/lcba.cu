@@ -226,7 +226,8 @@ extern "C" int lcba_create(lcba_t** out, int device) {
   // opt in to large dynamic shared memory (limit = opt-in size minus the kernel's static part)
   {
     const void* big_smem_kernels[] = {(const void*)k_linearize, (const void*)k_backsub,
-                                      (const void*)k_schur<true>, (const void*)k_schur<false>,
+                                      (const void*)k_schur<true, 160>, (const void*)k_schur<false, 160>,
+                                      (const void*)k_schur<true, 128>, (const void*)k_schur<false, 128>,
                                       (const void*)k_residual,
                                       (const void*)k_jdot,      (const void*)k_jacobian_blocks};
     for (const void* f : big_smem_kernels) {
@@ -640,15 +641,13 @@ static int pass_schur(lcba_t* h, const double* lam_host_or_null) {
   dim3 grid(pl.nslices, pl.nkinds);
   // sparse rigs skip duo blocks nobody sees; dense rigs run branch-free
   const bool skip = (double)h->N < 0.8 * (double)h->P * C;
-  if (skip) {
-    KL(h, "schur", k_schur<true><<<grid, pl.max_threads, pl.smem_bytes, h->stream>>>(
-          h->d_tab[w], h->d_pts[w], h->d_w, h->d_obs_start, h->d_mask, h->d_Lz, h->P, h->N, C, h->d_kinds,
-          h->d_hws, pl.nslices, pl.part_stride, pl.npairs, h->d_Spart));
-  } else {
-    KL(h, "schur", k_schur<false><<<grid, pl.max_threads, pl.smem_bytes, h->stream>>>(
-          h->d_tab[w], h->d_pts[w], h->d_w, h->d_obs_start, h->d_mask, h->d_Lz, h->P, h->N, C, h->d_kinds,
-          h->d_hws, pl.nslices, pl.part_stride, pl.npairs, h->d_Spart));
-  }
+#define LCBA_SCHUR_LAUNCH(SK, NR)                                                                   \
+  KL(h, "schur", (k_schur<SK, NR><<<grid, pl.max_threads, pl.smem_bytes, h->stream>>>(              \
+        h->d_tab[w], h->d_pts[w], h->d_w, h->d_obs_start, h->d_mask, h->d_Lz, h->P, h->N, C,        \
+        h->d_kinds, h->d_hws, pl.nslices, pl.part_stride, pl.npairs, h->d_Spart)))
+  if (pl.cfg == 0) { if (skip) LCBA_SCHUR_LAUNCH(true, 160); else LCBA_SCHUR_LAUNCH(false, 160); }
+  else             { if (skip) LCBA_SCHUR_LAUNCH(true, 128); else LCBA_SCHUR_LAUNCH(false, 128); }
+#undef LCBA_SCHUR_LAUNCH
   KL(h, "schur_reduce", k_reduce_cols<<<nblk((long long)pl.part_stride, 256), 256, 0, h->stream>>>(
         h->d_Spart, pl.nslices, (int)pl.part_stride, h->d_Sred));
   LCBA_TRY(allreduce(h, h->d_Sred, pl.part_stride, NCCL_SUM));

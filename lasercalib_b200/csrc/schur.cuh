@@ -21,9 +21,10 @@
 
 namespace lcba {
 
-constexpr int SCHUR_MAX_HW = 20;     // consumer half-warps (duo blocks) per CTA: 10 consumer + 2 producer
-                                     // warps x 160 registers (3 warps x 5120 regs per SM sub-partition)
-constexpr int SCHUR_PROD_WARPS = 2;
+constexpr int SCHUR_MAX_HW_A = 20;   // config A: 10 consumer + 2 producer warps x 160 registers
+constexpr int SCHUR_MAX_HW_B = 24;   // config B: 12 consumer + 4 producer warps x 128 registers
+constexpr int SCHUR_MAX_HW = 24;     // consumer half-warps (duo blocks) per CTA: 12 consumer + 4 producer
+                                     // warps x 128 registers: 3 consumers + 1 producer per SM sub-partition
 constexpr int SCHUR_STAGES = 2;
 constexpr int Y_LD = 50;             // doubles per (point, slot): 3 K-slices x 4 row groups x 4, +2 pad
 constexpr int JC_LD = 34;            // doubles per (point, diag slot): 2 K-slices x 16, +2 pad
@@ -49,6 +50,7 @@ struct SchurKind {
 struct SchurPlan {
   int C = 0, nkinds = 0, nslices = 0, pc = 0, max_threads = 0, max_slots = 0;
   int npairs = 0;
+  int cfg = 0;              // 0 = config A (12 warps x 160 regs), 1 = config B (16 warps x 128 regs)
   size_t part_stride = 0;   // doubles per slice partial: npairs*121 + 11*C
   size_t smem_bytes = 0;
   std::vector<SchurKind> kinds;
@@ -62,9 +64,12 @@ inline size_t schur_smem_bytes(int C, int pc, int nslots, int ndiag) {
           (size_t)C * CAMTAB) * 8 + 64;
 }
 
-inline SchurPlan make_schur_plan(int C, int sm_count, size_t smem_limit) {
+inline SchurPlan make_schur_plan_cfg(int C, int sm_count, size_t smem_limit, int cfg) {
   SchurPlan pl;
   pl.C = C;
+  pl.cfg = cfg;
+  const int max_hw = cfg ? SCHUR_MAX_HW_B : SCHUR_MAX_HW_A;
+  const int prod_warps = cfg ? 4 : 2;
   const int nb = (C + 1) / 2;
   pl.npairs = C * (C + 1) / 2;
   pl.part_stride = (size_t)pl.npairs * 121 + (size_t)NCP * C;
@@ -114,7 +119,7 @@ inline SchurPlan make_schur_plan(int C, int sm_count, size_t smem_limit) {
       }
       const int dg = (bj == bk) ? 1 : 0;
       // a kind with an odd number of diagonal blocks needs one idle half-warp
-      if ((int)blks.size() + 1 + ((nd + dg) & 1) > SCHUR_MAX_HW) { full = true; break; }
+      if ((int)blks.size() + 1 + ((nd + dg) & 1) > max_hw) { full = true; break; }
       nd += dg;
       freeb[bj][bk] = 0;
       --nfree;
@@ -165,7 +170,7 @@ inline SchurPlan make_schur_plan(int C, int sm_count, size_t smem_limit) {
     }
     K.nhw = (int)blks.size();
     const int cons_threads = 32 * ((K.nhw + 1) / 2);
-    K.threads = cons_threads + 32 * SCHUR_PROD_WARPS;
+    K.threads = cons_threads + 32 * prod_warps;
     K.qpr = cons_threads;                       // first producer thread
     pl.max_threads = std::max(pl.max_threads, K.threads);
     pl.max_slots = std::max(pl.max_slots, K.nslots);
@@ -183,6 +188,14 @@ inline SchurPlan make_schur_plan(int C, int sm_count, size_t smem_limit) {
   pl.nkinds = (int)pl.kinds.size();
   pl.nslices = std::max(1, sm_count / pl.nkinds);
   return pl;
+}
+
+// Config B holds 20 % more duo blocks per CTA but each CTA runs ~1.27x slower (measured on
+// B200): take it only when it saves enough kinds (e.g. 18 cameras: 2 kinds instead of 3).
+inline SchurPlan make_schur_plan(int C, int sm_count, size_t smem_limit) {
+  SchurPlan a = make_schur_plan_cfg(C, sm_count, smem_limit, 0);
+  SchurPlan b = make_schur_plan_cfg(C, sm_count, smem_limit, 1);
+  return (1.27 * b.nkinds < 1.0 * a.nkinds) ? b : a;
 }
 
 __device__ __forceinline__ void ld3(const double* __restrict__ p, double (&v)[3]) {
@@ -206,7 +219,7 @@ __device__ __forceinline__ void st4(double* p, double a, double b, double c, dou
 
 // Phase 1 for one (point, camera slot): Y = (Jc^T Jp) L^-T into Ys, Jc into Js (diagonal slots).
 // Invisible cameras produce exact zeros (w = 0, masked divide) so that phase 2 needs no
-// per-pair visibility test.  Branch-free: two of these are interleaved per producer thread.
+// per-pair visibility test.
 struct ProdIn {
   const double* T;
   double X[3], li[9], w;
@@ -265,8 +278,8 @@ __device__ __forceinline__ void nbar_arrive(int id, int count) {
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
-template <bool SKIP>
-__global__ void __maxnreg__(160)
+template <bool SKIP, int NREG>
+__global__ void __maxnreg__(NREG)
 k_schur(const double* __restrict__ tab, const double* __restrict__ pts,
         const double* __restrict__ wgt, const uint32_t* __restrict__ obs_start,
         const unsigned long long* __restrict__ mask, const double* __restrict__ Lz, long long P,
@@ -309,35 +322,26 @@ k_schur(const double* __restrict__ tab, const double* __restrict__ pts,
           reinterpret_cast<unsigned long long*>(s_J + (size_t)SP * ndiag * JC_LD);
       const long long q0 = pa + c * SP;
       const int npc = (int)min((long long)SP, pb - q0);
-      // two (point, slot) evaluations in flight per thread: loads first, then both chains
       const int total = npc * nslots;
-      for (int base = ptid; base < total; base += 2 * nprod) {
-        ProdIn in[2];
-        bool have[2];
+      for (int idx = ptid; idx < total; idx += nprod) {
+        ProdIn in;
+        const int q = idx / nslots, sl = idx - q * nslots;
+        const long long p = q0 + q;
+        const unsigned long long m = mask[p];
+        const int cam = K.slot_cam[sl];
+        const int ds = K.slot_dslot[sl];
+        in.live = (m >> cam) & 1ull;
+        in.w = 0.0;
+        if (in.live)
+          in.w = wgt ? wgt[(long long)obs_start[p] + __popcll(m & ((1ull << cam) - 1ull))] : 1.0;
+        in.T = s_tab + cam * CAMTAB;
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int idx = base + e * nprod;
-          have[e] = idx < total;
-          const int ii = have[e] ? idx : base;
-          const int q = ii / nslots, sl = ii - q * nslots;
-          const long long p = q0 + q;
-          const unsigned long long m = mask[p];
-          const int cam = K.slot_cam[sl];
-          const int ds = K.slot_dslot[sl];
-          in[e].live = (m >> cam) & 1ull;
-          in[e].w = 0.0;
-          if (in[e].live)
-            in[e].w = wgt ? wgt[(long long)obs_start[p] + __popcll(m & ((1ull << cam) - 1ull))] : 1.0;
-          in[e].T = s_tab + cam * CAMTAB;
+        for (int a = 0; a < 3; ++a) in.X[a] = pts[3 * p + a];
 #pragma unroll
-          for (int a = 0; a < 3; ++a) in[e].X[a] = pts[3 * p + a];
-#pragma unroll
-          for (int a = 0; a < 9; ++a) in[e].li[a] = Lz[p * 9 + a];
-          in[e].Y = s_Y + ((size_t)q * nslots + sl) * Y_LD;
-          in[e].Js = ds >= 0 ? s_J + ((size_t)q * ndiag + ds) * JC_LD : nullptr;
-        }
-        schur_produce(in[0]);
-        if (have[1]) schur_produce(in[1]);
+        for (int a = 0; a < 9; ++a) in.li[a] = Lz[p * 9 + a];
+        in.Y = s_Y + ((size_t)q * nslots + sl) * Y_LD;
+        in.Js = ds >= 0 ? s_J + ((size_t)q * ndiag + ds) * JC_LD : nullptr;
+        schur_produce(in);
       }
       for (int q = ptid; q < npc; q += nprod) s_mask[q] = mask[q0 + q];
       __threadfence_block();
