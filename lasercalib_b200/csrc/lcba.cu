@@ -645,7 +645,7 @@ static int pass_schur(lcba_t* h, const double* lam_host_or_null) {
   KL(h, "schur", (k_schur<SK, NR><<<grid, pl.max_threads, pl.smem_bytes, h->stream>>>(              \
         h->d_tab[w], h->d_pts[w], h->d_w, h->d_obs_start, h->d_mask, h->d_Lz, h->P, h->N, C,        \
         h->d_kinds, h->d_hws, pl.nslices, pl.part_stride, pl.npairs, h->d_Spart)))
-  if (pl.cfg == 0) { if (skip) LCBA_SCHUR_LAUNCH(true, 160); else LCBA_SCHUR_LAUNCH(false, 160); }
+  if (pl.cfg != 1) { if (skip) LCBA_SCHUR_LAUNCH(true, 160); else LCBA_SCHUR_LAUNCH(false, 160); }
   else             { if (skip) LCBA_SCHUR_LAUNCH(true, 128); else LCBA_SCHUR_LAUNCH(false, 128); }
 #undef LCBA_SCHUR_LAUNCH
   KL(h, "schur_reduce", k_reduce_cols<<<nblk((long long)pl.part_stride, 256), 256, 0, h->stream>>>(

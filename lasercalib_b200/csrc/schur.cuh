@@ -15,6 +15,7 @@
 //            inside a half-warp).
 // Partials per point-slice are written without atomics and summed in a fixed order.
 #pragma once
+#include <stdlib.h>
 #include <algorithm>
 #include <vector>
 #include "common.cuh"
@@ -68,8 +69,8 @@ inline SchurPlan make_schur_plan_cfg(int C, int sm_count, size_t smem_limit, int
   SchurPlan pl;
   pl.C = C;
   pl.cfg = cfg;
-  const int max_hw = cfg ? SCHUR_MAX_HW_B : SCHUR_MAX_HW_A;
-  const int prod_warps = cfg ? 4 : 2;
+  const int max_hw = cfg == 1 ? SCHUR_MAX_HW_B : (cfg == 2 ? 16 : SCHUR_MAX_HW_A);
+  const int prod_warps = cfg == 0 ? 2 : 4;
   const int nb = (C + 1) / 2;
   pl.npairs = C * (C + 1) / 2;
   pl.part_stride = (size_t)pl.npairs * 121 + (size_t)NCP * C;
@@ -195,6 +196,10 @@ inline SchurPlan make_schur_plan_cfg(int C, int sm_count, size_t smem_limit, int
 inline SchurPlan make_schur_plan(int C, int sm_count, size_t smem_limit) {
   SchurPlan a = make_schur_plan_cfg(C, sm_count, smem_limit, 0);
   SchurPlan b = make_schur_plan_cfg(C, sm_count, smem_limit, 1);
+  if (getenv("LCBA_SCHUR_CFG")) {
+    const int c = atoi(getenv("LCBA_SCHUR_CFG"));
+    return make_schur_plan_cfg(C, sm_count, smem_limit, c);
+  }
   return (1.27 * b.nkinds < 1.0 * a.nkinds) ? b : a;
 }
 
