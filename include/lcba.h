@@ -72,7 +72,10 @@ typedef struct lcba_options {
   int32_t max_iterations; /* >0: stop after this many outer iterations (bench: time exactly K) */
   int32_t fix_cameras;    /* 1: optimise the 3-D points only (PySBA.bundleAdjust_nocam,
                              pySBA.py:237-250): x = points, cameras stay at their values */
-  int32_t reserved[4];
+  int32_t shared_intrinsics; /* 1: one (f, k1, k2) for all cameras (PySBA.bundleAdjust_sharedcam,
+                                pySBA.py:252-325); the caller passes cameras whose columns 6..8
+                                are identical */
+  int32_t reserved[3];
 } lcba_options;
 
 /* One row of scipy's verbose=2 table (_lsq/common.py:545-563). */

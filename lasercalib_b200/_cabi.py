@@ -25,7 +25,7 @@ SYMBOLS = ["lcba_version", "lcba_create", "lcba_destroy", "lcba_last_error", "lc
 class Options(C.Structure):
     _fields_ = [("ftol", C.c_double), ("xtol", C.c_double), ("gtol", C.c_double),
                 ("max_nfev", C.c_int64), ("verbose", C.c_int32), ("profile", C.c_int32),
-                ("max_iterations", C.c_int32), ("fix_cameras", C.c_int32), ("reserved", C.c_int32 * 4)]
+                ("max_iterations", C.c_int32), ("fix_cameras", C.c_int32), ("shared_intrinsics", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
 class TraceRow(C.Structure):
@@ -207,7 +207,7 @@ class Engine:
 
     # ---- solver ----
     def solve(self, ftol=1e-8, xtol=1e-8, gtol=1e-8, max_nfev=0, verbose=0, profile=False,
-              max_iterations=0, fix_cameras=False):
+              max_iterations=0, fix_cameras=False, shared_intrinsics=False):
         opt = Options()
         self.lib.lcba_default_options(C.byref(opt))
         opt.ftol, opt.xtol, opt.gtol = ftol, xtol, gtol
@@ -216,6 +216,7 @@ class Engine:
         opt.profile = 1 if profile else 0
         opt.max_iterations = int(max_iterations or 0)
         opt.fix_cameras = 1 if fix_cameras else 0
+        opt.shared_intrinsics = 1 if shared_intrinsics else 0
         res = Result()
         self._check(self.lib.lcba_solve(self.h, C.byref(opt), C.byref(res)))
         rows = (TraceRow * LCBA_MAX_TRACE)()

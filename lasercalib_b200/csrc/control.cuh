@@ -122,8 +122,18 @@ __device__ inline void ctl_solve_subspace(Ctl* c) {
 __global__ void __launch_bounds__(256)
 k_ctl_lin(const double* __restrict__ camsum, const double* __restrict__ cams,
           double* __restrict__ scl_c, double* __restrict__ gt_c, double* __restrict__ g_c, int C,
-          Ctl* __restrict__ ctl, int first, int fix_cameras) {
+          Ctl* __restrict__ ctl, int first, int fix_cameras, int shared_intr) {
   __shared__ double s_red[32];
+  __shared__ double s_sh[6];   // shared-intrinsics mode: summed gradient / diag of (f, k1, k2)
+  if (shared_intr) {
+    if (threadIdx.x < 6) {
+      const int a = 6 + threadIdx.x % 3, off = threadIdx.x < 3 ? 0 : 11;
+      double sum = 0.0;
+      for (int c = 0; c < C; ++c) sum += camsum[c * 22 + off + a];
+      s_sh[threadIdx.x] = sum;
+    }
+    __syncthreads();
+  }
   double gh2 = 0, xs2 = 0, x2 = 0, gmax = 0;
   for (int i = threadIdx.x; i < C * NCP; i += blockDim.x) {
     const int c = i / NCP, a = i % NCP;
@@ -131,9 +141,14 @@ k_ctl_lin(const double* __restrict__ camsum, const double* __restrict__ cams,
       scl_c[i] = 1.0; g_c[i] = 0.0; gt_c[i] = 0.0;
       continue;
     }
-    const double g = camsum[c * 22 + a];
-    double s = sqrt(camsum[c * 22 + 11 + a]);
+    const bool sh = shared_intr && a >= 6 && a <= 8;   // one parameter replicated over cameras
+    const double g = sh ? s_sh[a - 6] : camsum[c * 22 + a];
+    double s = sqrt(sh ? s_sh[3 + a - 6] : camsum[c * 22 + 11 + a]);
     if (first) { if (s == 0.0) s = 1.0; } else s = fmax(s, scl_c[i]);
+    if (sh && c > 0) {          // replicas carry the values but count once in the norms
+      scl_c[i] = s; g_c[i] = g; gt_c[i] = g / s / s;
+      continue;
+    }
     scl_c[i] = s;
     g_c[i] = g;
     const double gh = g / s, x = cams[i];
@@ -190,10 +205,11 @@ __global__ void __launch_bounds__(256)
 k_ctl_sub(const double* __restrict__ red, const double* __restrict__ g_c,
           const double* __restrict__ gt_c, const double* __restrict__ pc,
           const double* __restrict__ scl_c, int C, Ctl* __restrict__ ctl,
-          const int* __restrict__ chol_fail, double* __restrict__ coef) {
+          const int* __restrict__ chol_fail, double* __restrict__ coef, int shared_intr) {
   __shared__ double s_red[32];
   double v[6] = {0, 0, 0, 0, 0, 0};
   for (int i = threadIdx.x; i < C * NCP; i += blockDim.x) {
+    if (shared_intr && i >= NCP && i % NCP >= 6 && i % NCP <= 8) continue;   // replicas
     const double s = scl_c[i];
     const double ah = g_c[i] / s, bh = pc[i] * s, gt = gt_c[i], p = pc[i];
     v[0] = fma(ah, ah, v[0]); v[1] = fma(ah, bh, v[1]); v[2] = fma(bh, bh, v[2]);

@@ -103,7 +103,8 @@ struct lcba_handle {
   // comm
   ncclComm_t comm = nullptr;
   int rank = 0, nranks = 1;
-  int fix_cameras = 0;
+  int fix_cameras = 0, shared_intr = 0;
+  double *d_pred = nullptr, *d_scl_red = nullptr;   // shared-intrinsics mode: reduced step / scale
 };
 
 static std::string g_last_error;
@@ -397,6 +398,8 @@ extern "C" int lcba_set_problem(lcba_t* h, int32_t C, int64_t P, int64_t N, cons
   LCBA_TRY(dev_alloc(h, &h->d_gt_c, (size_t)n));
   LCBA_TRY(dev_alloc(h, &h->d_g_c, (size_t)n));
   LCBA_TRY(dev_alloc(h, &h->d_pc, (size_t)n));
+  LCBA_TRY(dev_alloc(h, &h->d_pred, (size_t)n));
+  LCBA_TRY(dev_alloc(h, &h->d_scl_red, (size_t)n));
   LCBA_TRY(dev_alloc(h, &h->d_S, (size_t)n * n));
   LCBA_TRY(dev_alloc(h, &h->d_Lf, (size_t)n * n));
   LCBA_TRY(dev_alloc(h, &h->d_rhs, (size_t)n));
@@ -607,7 +610,7 @@ static int pass_linearize(lcba_t* h, int first) {
   LCBA_TRY(allreduce(h, h->d_camsum, (size_t)C * CAMSUM + 1 + 3, NCCL_SUM));
   LCBA_TRY(allreduce(h, pp + 3, 1, NCCL_MAX));
   KL(h, "ctl", k_ctl_lin<<<1, 256, 0, h->stream>>>(h->d_camsum, h->d_cams[w], h->d_scl_c, h->d_gt_c,
-                                                   h->d_g_c, C, h->d_ctl, first, h->fix_cameras));
+                                                   h->d_g_c, C, h->d_ctl, first, h->fix_cameras, h->shared_intr));
   KL(h, "ctl", k_ctl_lin2<<<1, 1, 0, h->stream>>>(pp, h->d_ctl, first));
   return check_launch(h, "linearize pass");
 }
@@ -651,7 +654,13 @@ static int pass_schur(lcba_t* h, const double* lam_host_or_null) {
   KL(h, "schur_reduce", k_reduce_cols<<<nblk((long long)pl.part_stride, 256), 256, 0, h->stream>>>(
         h->d_Spart, pl.nslices, (int)pl.part_stride, h->d_Sred));
   LCBA_TRY(allreduce(h, h->d_Sred, pl.part_stride, NCCL_SUM));
-  if (lam_host_or_null) {
+  if (h->shared_intr) {
+    const int nr = 3 + 8 * C;
+    KL(h, "assemble", k_assemble_S_shared<<<nblk((long long)nr * nr, 256), 256, 0, h->stream>>>(
+          h->d_Sred, C, pl.npairs, h->d_camsum, h->d_scl_c, h->d_ctl,
+          lam_host_or_null ? *lam_host_or_null : 0.0, lam_host_or_null ? 0 : 1, h->d_S, h->d_rhs,
+          h->d_scl_red));
+  } else if (lam_host_or_null) {
     KL(h, "assemble", k_assemble_S<<<nblk((long long)n * n, 256), 256, 0, h->stream>>>(
           h->d_Sred, C, pl.npairs, h->d_camsum, h->d_scl_c, *lam_host_or_null, h->d_S, h->d_rhs));
   } else {
@@ -719,10 +728,10 @@ __global__ void k_assemble_S_ctl(const double* __restrict__ red, int C, int npai
 
 // Cholesky of S + mu*Dc^2, solve for the camera step
 static int pass_camera_solve(lcba_t* h, double mu) {
-  const int n = h->C * NCP;
+  const int n = h->shared_intr ? 3 + 8 * h->C : h->C * NCP;
   LCBA_CUDA(h, cudaMemsetAsync(h->d_fail, 0, sizeof(int), h->stream));
   KL(h, "chol_copy", k_copy_damped<<<nblk((long long)n * n, 256), 256, 0, h->stream>>>(
-        h->d_S, n, mu, h->d_scl_c, h->d_Lf));
+        h->d_S, n, mu, h->shared_intr ? h->d_scl_red : h->d_scl_c, h->d_Lf));
   for (int k = 0; k < n; k += CH_NB) {
     KL(h, "chol_panel", k_chol_panel<<<1, 256, 0, h->stream>>>(h->d_Lf, n, k, h->d_fail));
     const int rem = n - k - CH_NB;
@@ -731,7 +740,12 @@ static int pass_camera_solve(lcba_t* h, double mu) {
       KL(h, "chol_update", k_chol_update<<<dim3(nt, nt), 256, 0, h->stream>>>(h->d_Lf, n, k));
     }
   }
-  KL(h, "chol_solve", k_chol_solve<<<1, 256, (size_t)n * 8, h->stream>>>(h->d_Lf, n, h->d_rhs, h->d_pc));
+  if (h->shared_intr) {
+    KL(h, "chol_solve", k_chol_solve<<<1, 256, (size_t)n * 8, h->stream>>>(h->d_Lf, n, h->d_rhs, h->d_pred));
+    KL(h, "expand", k_expand_shared<<<nblk(h->C * NCP, 128), 128, 0, h->stream>>>(h->d_pred, h->C, h->d_pc));
+  } else {
+    KL(h, "chol_solve", k_chol_solve<<<1, 256, (size_t)n * 8, h->stream>>>(h->d_Lf, n, h->d_rhs, h->d_pc));
+  }
   return check_launch(h, "camera solve");
 }
 
@@ -744,7 +758,7 @@ static int pass_backsub(lcba_t* h) {
   KL(h, "reduce", k_reduce_scalars<<<BS_K, 256, 0, h->stream>>>(h->d_part, h->lin_grid, BS_K, h->d_red, BS_K));
   LCBA_TRY(allreduce(h, h->d_red, BS_K, NCCL_SUM));
   KL(h, "ctl", k_ctl_sub<<<1, 256, 0, h->stream>>>(h->d_red, h->d_g_c, h->d_gt_c, h->d_pc, h->d_scl_c, C,
-                                                   h->d_ctl, h->d_fail, h->d_coef));
+                                                   h->d_ctl, h->d_fail, h->d_coef, h->shared_intr));
   return check_launch(h, "backsub pass");
 }
 
@@ -796,7 +810,9 @@ extern "C" int lcba_solve(lcba_t* h, const lcba_options* opt_in, lcba_result* re
     h->P_total = (long long)(v + 0.5);
   }
   h->fix_cameras = opt.fix_cameras ? 1 : 0;
-  const long long n_total = (h->fix_cameras ? 0 : (long long)h->C * NCP) + 3 * h->P_total;
+  h->shared_intr = (opt.shared_intrinsics && !h->fix_cameras) ? 1 : 0;
+  const long long n_cam = h->fix_cameras ? 0 : (h->shared_intr ? 3 + 8LL * h->C : (long long)h->C * NCP);
+  const long long n_total = n_cam + 3 * h->P_total;
   const long long max_nfev = opt.max_nfev > 0 ? opt.max_nfev : 100 * n_total;
 
   cudaEvent_t t0, t1;
@@ -995,6 +1011,7 @@ extern "C" int lcba_linearize(lcba_t* h, double lam, double* S_out, double* rhs_
   init.term = -1;
   LCBA_CUDA(h, cudaMemcpyAsync(h->d_ctl, &init, sizeof(Ctl), cudaMemcpyHostToDevice, h->stream));
   h->fix_cameras = 0;
+  h->shared_intr = 0;
   LCBA_TRY(pass_linearize(h, 1));
   LCBA_TRY(pass_schur(h, &lam));
   const int n = h->C * NCP;

@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <vector>
 #include "common.cuh"
+#include "control.cuh"
 
 namespace lcba {
 
@@ -472,6 +473,62 @@ __global__ void k_assemble_S(const double* __restrict__ red, int C, int npairs,
     rhs[r] = camsum[(r / NCP) * 22 + (r % NCP)] + red[(size_t)npairs * 121 + r];
   }
   S[idx] = v;
+}
+
+
+// ---- shared intrinsics (PySBA.bundleAdjust_sharedcam, pySBA.py:252-325) -------------------
+// Reduced parameter order of the reference: [f k1 k2 | 6 extrinsics per camera | cx cy per
+// camera].  J_red = J_full T with a 0/1 matrix T, so S_red = T^T S_full T (+ damping once per
+// reduced parameter) and rhs_red = T^T rhs_full.
+__host__ __device__ inline int shared_red_index(int c, int a, int C) {
+  return a < 6 ? 3 + 6 * c + a : (a < 9 ? a - 6 : 3 + 6 * C + 2 * c + (a - 9));
+}
+
+__device__ __forceinline__ double sfull_entry(const double* __restrict__ red, int r, int c) {
+  const int hi = max(r, c), lo = min(r, c);
+  const int j = hi / NCP, a = hi % NCP, k = lo / NCP, b = lo % NCP;
+  if (j == k) return red[(size_t)(j * (j + 1) / 2 + j) * 121 + (r % NCP) * NCP + (c % NCP)];
+  return red[(size_t)(j * (j + 1) / 2 + k) * 121 + a * NCP + b];
+}
+
+// preimage of reduced index i: cameras [c0, c1) and the full parameter slot a
+__device__ __forceinline__ void shared_preimage(int i, int C, int& c0, int& c1, int& a) {
+  if (i < 3) { c0 = 0; c1 = C; a = 6 + i; }
+  else if (i < 3 + 6 * C) { c0 = (i - 3) / 6; c1 = c0 + 1; a = (i - 3) % 6; }
+  else { c0 = (i - 3 - 6 * C) / 2; c1 = c0 + 1; a = 9 + (i - 3 - 6 * C) % 2; }
+}
+
+__global__ void k_assemble_S_shared(const double* __restrict__ red, int C, int npairs,
+                                    const double* __restrict__ camsum,
+                                    const double* __restrict__ scl_c, const Ctl* __restrict__ ctl,
+                                    double lam_host, int use_ctl, double* __restrict__ S,
+                                    double* __restrict__ rhs, double* __restrict__ scl_red) {
+  const double lam = use_ctl ? ctl->reg_term : lam_host;
+  const int n = 3 + 8 * C;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)n * n) return;
+  const int i = (int)(idx / n), j = (int)(idx % n);
+  int ic0, ic1, ia, jc0, jc1, ja;
+  shared_preimage(i, C, ic0, ic1, ia);
+  shared_preimage(j, C, jc0, jc1, ja);
+  double v = 0.0;
+  for (int c = ic0; c < ic1; ++c)
+    for (int d = jc0; d < jc1; ++d) v += sfull_entry(red, c * NCP + ia, d * NCP + ja);
+  if (i == j) {
+    const double s = scl_c[ic0 * NCP + ia];
+    scl_red[i] = s;
+    v = fma(lam * s, s, v);
+    double r = 0.0;
+    for (int c = ic0; c < ic1; ++c)
+      r += camsum[c * 22 + ia] + red[(size_t)npairs * 121 + c * NCP + ia];
+    rhs[i] = r;
+  }
+  S[idx] = v;
+}
+
+__global__ void k_expand_shared(const double* __restrict__ p_red, int C, double* __restrict__ pc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < C * NCP) pc[i] = p_red[shared_red_index(i / NCP, i % NCP, C)];
 }
 
 }  // namespace lcba

@@ -195,7 +195,7 @@ class PySBA:
 
     # ---- solver (pySBA.py:132-147) ----
     def bundleAdjust(self, ftol=1e-4, xtol=1e-8, gtol=1e-8, max_nfev=None, verbose=2,
-                     profile=False, max_iterations=0, _fix_cameras=False):
+                     profile=False, max_iterations=0, _fix_cameras=False, _shared=False):
         """Returns the bundle adjusted parameters (scipy ``OptimizeResult`` layout) and
         stores them on ``self.cameraArray`` / ``self.points3D``.
 
@@ -206,6 +206,10 @@ class PySBA:
         numPoints = self.points3D.shape[0]
         cams0 = np.ascontiguousarray(self.cameraArray, dtype=np.float64)
         pts0 = np.ascontiguousarray(self.points3D, dtype=np.float64)
+        if _shared:
+            # x0 of the reference: the mean (f, k1, k2) for every camera (pySBA.py:300)
+            cams0 = cams0.copy()
+            cams0[:, 6:9] = np.mean(cams0[:, 6:9], axis=0)
         rank, ws, _ = _dist.world()
         shard = None
         if ws > 1:
@@ -226,12 +230,13 @@ class PySBA:
         else:
             eng = self._ensure_problem(cams0, pts0, self.cameraIndices, self.point2DIndices,
                                        self.points2D, self._pointWeights)
-            if not self._fresh_problem:        # observations already resident: new x0 only
+            if not self._fresh_problem or _shared:   # observations already resident: new x0 only
                 eng.set_params(cams0, pts0)
         try:
             res, trace = eng.solve(ftol=ftol, xtol=xtol, gtol=gtol, max_nfev=max_nfev or 0,
                                    verbose=verbose, profile=profile,
-                                   max_iterations=max_iterations, fix_cameras=_fix_cameras)
+                                   max_iterations=max_iterations, fix_cameras=_fix_cameras,
+                                   shared_intrinsics=_shared)
         except _cabi.LcbaError as e:
             if e.code == -5:
                 raise ValueError("Residuals are not finite in the initial point.") from e
@@ -246,6 +251,22 @@ class PySBA:
             pts = _dist.allgather_rows(pts, shard["bounds"])
         if _fix_cameras:
             return self._finish_nocam(eng, res, pts, shard, verbose)
+        if _shared:
+            # the reference's parameter order: [f k1 k2 | extrinsics | centroids | points]
+            x = np.hstack((cams[0, 6:9], cams[:, :6].ravel(), cams[:, 9:].ravel(), pts.ravel()))
+            out = BAResult(x=x, cost=res.cost, optimality=res.optimality,
+                           active_mask=np.zeros_like(x), nfev=int(res.nfev), njev=int(res.njev),
+                           status=int(res.status))
+            out["message"] = TERMINATION_MESSAGES[int(res.status)]
+            out["success"] = int(res.status) > 0
+            out["solve_ms"] = res.solve_ms
+            out["nit"] = int(res.iterations)
+            out.set_lazy("fun", lambda: eng.residuals(None)[0])
+            if verbose >= 1:
+                print(out["message"])
+            self.cameraArray = cams
+            self.points3D = pts
+            return out
         x = np.hstack((cams.ravel(), pts.ravel()))
         out = BAResult(x=x, cost=res.cost, optimality=res.optimality,
                        active_mask=np.zeros_like(x), nfev=int(res.nfev), njev=int(res.njev),
@@ -327,7 +348,10 @@ class PySBA:
         return self.bundleAdjust(ftol, _fix_cameras=True)
 
     def bundleAdjust_sharedcam(self, ftol=1e-6):
-        self._next_row("bundleAdjust_sharedcam")
+        """Bundle adjustment with one (f, k1, k2) shared by all cameras (pySBA.py:286-325).
+        Returns x in the reference's order [f k1 k2 | 6 extrinsics per camera | cx cy per
+        camera | points]; ``cameraArray`` gets the shared intrinsics tiled."""
+        return self.bundleAdjust(ftol, _shared=True)
 
     def bundleAdjust_transform_points_3d(self, ftol=1e-3):
         self._next_row("bundleAdjust_transform_points_3d")

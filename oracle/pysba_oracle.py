@@ -582,6 +582,145 @@ def trf_exact_nocam(cams, pts, points_2d, camera_indices, point_indices, weights
                           status=status or 0, trace=trace)
 
 
+# ------------------------------------------------------- shared intrinsics (pySBA.py:252-325)
+def sharedcam_pack(cams, pts):
+    """x0 of ``bundleAdjust_sharedcam``: [mean(f,k1,k2) | extrinsics C*6 | centroids C*2 | points]."""
+    return np.hstack((np.mean(cams[:, 6:9], axis=0).ravel(), cams[:, :6].ravel(),
+                      cams[:, 9:].ravel(), pts.ravel()))
+
+
+def sharedcam_unpack(x, C, P):
+    sh = x[:3]
+    ext = x[3:3 + 6 * C].reshape(C, 6)
+    cen = x[3 + 6 * C:3 + 8 * C].reshape(C, 2)
+    cams = np.concatenate((ext, np.tile(sh, (C, 1)), cen), axis=1)
+    return cams, x[3 + 8 * C:].reshape(P, 3)
+
+
+def fun_sharedcam(params, n_cameras, n_points, camera_indices, point_indices, points_2d, weights):
+    cams, pts = sharedcam_unpack(params, n_cameras, n_points)
+    uv = project(pts[point_indices], cams[camera_indices])
+    return (weights * (uv - points_2d)).ravel()
+
+
+def sparsity_sharedcam(n_cameras, n_points, camera_indices, point_indices):
+    """pySBA.py:252-276: every row sees the 3 shared columns, 6 + 2 own camera columns, 3 point
+    columns."""
+    N, C = camera_indices.size, n_cameras
+    cols = np.empty((N, 14), dtype=np.int64)
+    cols[:, 0:3] = np.arange(3)
+    cols[:, 3:9] = 3 + camera_indices[:, None] * 6 + np.arange(6)
+    cols[:, 9:11] = 3 + 6 * C + camera_indices[:, None] * 2 + np.arange(2)
+    cols[:, 11:14] = 3 + 8 * C + point_indices[:, None] * 3 + np.arange(3)
+    cols = np.repeat(cols[:, None, :], 2, axis=1)
+    return csr_matrix((np.ones(cols.size, dtype=int), cols.ravel(),
+                       np.arange(0, 28 * N + 1, 14, dtype=np.int64)),
+                      shape=(2 * N, 3 + 8 * C + 3 * n_points))
+
+
+def bundle_adjust_sharedcam(cams, pts, points_2d, camera_indices, point_indices, weights=None,
+                            ftol=1e-6, verbose=0, **ls_kwargs):
+    """The reference's ``bundleAdjust_sharedcam`` (pySBA.py:286-325) through scipy."""
+    C, P = cams.shape[0], pts.shape[0]
+    if weights is None:
+        weights = default_weights(point_indices)
+    weights = np.asarray(weights).reshape(-1, 1)
+    A = sparsity_sharedcam(C, P, camera_indices, point_indices)
+    return least_squares(fun_sharedcam, sharedcam_pack(cams, pts), jac_sparsity=A, verbose=verbose,
+                         x_scale="jac", ftol=ftol, method="trf", jac="3-point",
+                         args=(C, P, camera_indices, point_indices, points_2d, weights), **ls_kwargs)
+
+
+def trf_exact_generic(fun_x, jac_x, x0, ftol, xtol=1e-8, gtol=1e-8, max_nfev=None):
+    """``trf_no_bounds`` with an analytic sparse Jacobian ``jac_x(x)`` (CSR) and the exact
+    solution of (J_h^T J_h + reg_term I) p = J_h^T f by sparse LU.  Same restatement as
+    ``trf_exact`` for any parameterisation."""
+    from numpy.linalg import norm
+    from scipy.linalg import qr
+    from scipy.optimize._lsq.common import (check_termination, minimize_quadratic_1d,
+                                            solve_trust_region_2d, update_tr_radius)
+    from scipy.sparse import diags, identity
+    from scipy.sparse.linalg import splu
+    x = np.asarray(x0, dtype=np.float64).copy()
+    f = fun_x(x)
+    if not np.all(np.isfinite(f)):
+        raise ValueError("Residuals are not finite in the initial point.")
+    J = jac_x(x)
+    nfev = njev = 1
+    cost = 0.5 * f @ f
+    g = J.T @ f
+    scale_inv = np.sqrt(np.asarray(J.power(2).sum(axis=0)).ravel())
+    scale_inv[scale_inv == 0] = 1
+    Delta = norm(x * scale_inv) or 1.0
+    if max_nfev is None:
+        max_nfev = x.size * 100
+    status, trace = None, []
+    while True:
+        g_norm = norm(g, ord=np.inf)
+        if g_norm < gtol:
+            status = 1
+        trace.append(cost)
+        if status is not None or nfev == max_nfev:
+            break
+        d = 1 / scale_inv
+        Jh = J @ diags(d)
+        g_h = d * g
+        Jg = Jh @ g_h
+        reg = -minimize_quadratic_1d(0.5 * Jg @ Jg, -g_h @ g_h, 0, Delta / norm(g_h))[1] / Delta**2
+        gn_h = splu((Jh.T @ Jh + reg * identity(x.size)).tocsc()).solve(Jh.T @ f)
+        Sq, _ = qr(np.vstack((g_h, gn_h)).T, mode="economic")
+        JS = Jh @ Sq
+        B_S, g_S = JS.T @ JS, Sq.T @ g_h
+        actual = -1
+        while actual <= 0 and nfev < max_nfev:
+            p_S, _ = solve_trust_region_2d(B_S, g_S, Delta)
+            step_h = Sq @ p_S
+            Js = JS @ p_S
+            pred = -(0.5 * Js @ Js + step_h @ g_h)
+            x_new = x + d * step_h
+            f_new = fun_x(x_new)
+            nfev += 1
+            shn = norm(step_h)
+            if not np.all(np.isfinite(f_new)):
+                Delta = 0.25 * shn
+                continue
+            cost_new = 0.5 * f_new @ f_new
+            actual = cost - cost_new
+            Delta_new, ratio = update_tr_radius(Delta, actual, pred, shn, shn > 0.95 * Delta)
+            status = check_termination(actual, cost, norm(d * step_h), norm(x), ratio, ftol, xtol)
+            if status is not None:
+                break
+            Delta = Delta_new
+        if actual > 0:
+            x, f, cost = x_new, f_new, cost_new
+            J = jac_x(x)
+            njev += 1
+            g = J.T @ f
+            scale_inv = np.maximum(np.sqrt(np.asarray(J.power(2).sum(axis=0)).ravel()), scale_inv)
+    return OptimizeResult(x=x, cost=cost, fun=f, grad=g, optimality=g_norm, nfev=nfev, njev=njev,
+                          status=status or 0, trace=trace)
+
+
+def trf_exact_sharedcam(cams, pts, points_2d, camera_indices, point_indices, weights=None,
+                        ftol=1e-6, **kw):
+    """Exact-solve TRF in the shared-intrinsics parameterisation: J_red = J_full T."""
+    C, P = cams.shape[0], pts.shape[0]
+    if weights is None:
+        weights = default_weights(point_indices)
+    weights = np.asarray(weights).reshape(-1, 1)
+    args = (C, P, camera_indices, point_indices, points_2d, weights)
+    A = sparsity_sharedcam(C, P, camera_indices, point_indices)
+
+    def jac(x):
+        cm, pt = sharedcam_unpack(x, C, P)
+        _, Jc, Jp = jacobian_blocks(cm, pt, camera_indices, point_indices, weights)
+        data = np.concatenate([Jc[:, :, 6:9], Jc[:, :, 0:6], Jc[:, :, 9:11], Jp], axis=2).reshape(-1)
+        return csr_matrix((data, A.indices, A.indptr), shape=A.shape)
+
+    return trf_exact_generic(lambda x: fun_sharedcam(x, *args), jac, sharedcam_pack(cams, pts),
+                             ftol, **kw)
+
+
 def rmse_px(res_vec):
     """sqrt(mean(|r_i|^2)) over observations, r_i the 2-vector pixel residual."""
     r = np.asarray(res_vec).reshape(-1, 2)

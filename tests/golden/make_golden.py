@@ -191,6 +191,20 @@ def golden_nocam():
     print("ba_nocam_ring8_600: cost", res.cost, "nfev", res.nfev, "status", res.status)
 
 
+def golden_sharedcam():
+    """PySBA.bundleAdjust_sharedcam (pySBA.py:286-325) on an 8-camera rig."""
+    pb = make_rig("ring8", 500, seed=12, variant="volume", p_vis=0.8)
+    sba = PySBA(pb["cams0"].copy(), pb["pts0"].copy(), pb["points_2d"], pb["camera_ind"],
+                pb["point_ind"])
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        res = sba.bundleAdjust_sharedcam(1e-6)
+    np.savez_compressed(os.path.join(HERE, "ba_sharedcam_ring8_500.npz"), ref_x=res.x,
+                        ref_cost=res.cost, ref_nfev=res.nfev, ref_status=res.status,
+                        ref_cams=sba.cameraArray, ref_log=buf.getvalue(), **inputs_of(pb), **VERS)
+    print("ba_sharedcam_ring8_500: cost", res.cost, "nfev", res.nfev, "status", res.status)
+
+
 def golden_io():
     """Export / init formats of lasercalib/convert_params.py on the 17 example cameras."""
     import cv2
@@ -214,6 +228,9 @@ def golden_io():
 
 
 if __name__ == "__main__":
+    if "--only-sharedcam" in sys.argv:
+        golden_sharedcam()
+        sys.exit(0)
     if "--only-io" in sys.argv:
         golden_io()
         sys.exit(0)
@@ -221,6 +238,7 @@ if __name__ == "__main__":
         golden_nocam()
         sys.exit(0)
     golden_nocam()
+    golden_sharedcam()
     golden_model()
     golden_example_cams()
     golden_ba("ba_ring4_planar2000", "ring4", 2000, "planar")

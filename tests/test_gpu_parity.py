@@ -336,6 +336,30 @@ def test_bundleAdjust_nocam_points_only(PySBA, golden):
     assert res.grad.shape == res.x.shape
 
 
+def test_bundleAdjust_sharedcam(PySBA, golden):
+    """PySBA.bundleAdjust_sharedcam (pySBA.py:286-325) — one (f, k1, k2)."""
+    g = golden("ba_sharedcam_ring8_500")
+    C, P = g["cams0"].shape[0], g["pts0"].shape[0]
+    args = (g["cams0"], g["pts0"], g["points_2d"], g["camera_ind"], g["point_ind"])
+    ora = O.trf_exact_sharedcam(*args, ftol=1e-4)
+    sba = PySBA(g["cams0"].copy(), g["pts0"].copy(), g["points_2d"], g["camera_ind"], g["point_ind"])
+    res = sba.bundleAdjust_sharedcam(1e-4)
+    assert res.x.shape == (3 + 8 * C + 3 * P,)
+    assert np.all(sba.cameraArray[:, 6:9] == sba.cameraArray[0, 6:9])      # intrinsics stay tied
+    np.testing.assert_array_equal(res.x[:3], sba.cameraArray[0, 6:9])
+    assert res.nfev == ora.nfev and res.status == ora.status
+    np.testing.assert_allclose(res.cost, ora.cost, rtol=1e-8)
+    np.testing.assert_allclose(res.x[:3], ora.x[:3], rtol=1e-5)
+    w = O.default_weights(g["point_ind"])
+    f = O.fun_sharedcam(res.x, C, P, g["camera_ind"], g["point_ind"], g["points_2d"], w)
+    np.testing.assert_allclose(0.5 * f @ f, res.cost, rtol=1e-10)
+    # run to the reference's own tolerance: the exact solver ends at or below the reference cost
+    sba2 = PySBA(g["cams0"].copy(), g["pts0"].copy(), g["points_2d"], g["camera_ind"], g["point_ind"])
+    res2 = sba2.bundleAdjust_sharedcam(1e-6)
+    assert res2.cost <= float(g["ref_cost"]) * (1 + 1e-9)
+    np.testing.assert_allclose(res2.cost, float(g["ref_cost"]), rtol=2e-3)
+
+
 # ----------------------------------------------------------------------------- error paths
 def test_error_behaviour(PySBA, Engine):
     from lasercalib_b200._cabi import LcbaError
@@ -359,7 +383,7 @@ def test_error_behaviour(PySBA, Engine):
     with pytest.raises(LcbaError, match="64 cameras"):
         eng.set_problem(np.zeros((65, 11)), pb["pts0"], pb["points_2d"], pb["camera_ind"], pb["point_ind"])
     with pytest.raises(NotImplementedError):
-        sba.bundleAdjust_sharedcam()
+        sba.bundle_adjustment_camonly()
     eng.close()
 
 
