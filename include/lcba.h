@@ -138,6 +138,14 @@ int lcba_rotate(lcba_t* h, int64_t M, const double* pts, const double* rot_vecs,
 int lcba_project(lcba_t* h, int64_t M, const double* pts, const double* cams_rows,
                  double* out_uv);
 
+/* ---- 3-D initialisation: Unproject (lasercalib/rigid_body.py:205-243) -----------------
+ * Pixels of the reference camera -> world points on the plane(s) z = Z: OpenCV's iterative
+ * undistortPoints (5 iterations) + ray/plane intersection.  camera_matrix 3x3 row-major,
+ * dist 5 (k1 k2 p1 p2 k3), rc_ext 3x3 row-major, tc_ext 3; Z has nZ = 1 or M entries. */
+int lcba_unproject(lcba_t* h, int64_t M, const double* uv, const double* Z, int64_t nZ,
+                   const double* camera_matrix, const double* dist5, const double* rc_ext,
+                   const double* tc_ext, double* out_xyz);
+
 /* ---- PySBA.fun (pySBA.py:92-101) --------------------------------------------------
  * x_or_null: 11C + 3P parameters (NULL = the handle's current x). r_out: 2N or NULL. */
 int lcba_residuals(lcba_t* h, const double* x_or_null, double* r_out, double* cost_out);

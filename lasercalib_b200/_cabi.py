@@ -17,7 +17,7 @@ E_NAMES = {-1: "LCBA_E_ARG", -2: "LCBA_E_CUDA", -3: "LCBA_E_STATE", -4: "LCBA_E_
 # every symbol include/lcba.h declares (tests/test_cabi.py checks the export list)
 SYMBOLS = ["lcba_version", "lcba_create", "lcba_destroy", "lcba_last_error", "lcba_default_options",
            "lcba_set_problem", "lcba_set_params", "lcba_get_params", "lcba_rotate", "lcba_project",
-           "lcba_residuals", "lcba_jacobian_blocks", "lcba_sparsity_indices", "lcba_solve",
+           "lcba_unproject", "lcba_residuals", "lcba_jacobian_blocks", "lcba_sparsity_indices", "lcba_solve",
            "lcba_get_trace", "lcba_get_grad", "lcba_get_profile", "lcba_linearize",
            "lcba_time_device", "lcba_nccl_unique_id", "lcba_comm_init", "lcba_debug_tr2d"]
 
@@ -79,6 +79,7 @@ def load():
     lib.lcba_get_params.argtypes = [vp, vp, vp]
     lib.lcba_rotate.argtypes = [vp, i64, vp, vp, vp]
     lib.lcba_project.argtypes = [vp, i64, vp, vp, vp]
+    lib.lcba_unproject.argtypes = [vp, i64, vp, vp, i64, vp, vp, vp, vp, vp]
     lib.lcba_residuals.argtypes = [vp, vp, vp, pd]
     lib.lcba_jacobian_blocks.argtypes = [vp, vp, vp, vp]
     lib.lcba_sparsity_indices.argtypes = [vp, i32, i64, i64, vp, vp, vp]
@@ -180,6 +181,19 @@ class Engine:
         out = np.empty((points.shape[0], 2))
         self._check(self.lib.lcba_project(self.h, points.shape[0], _ptr(points), _ptr(cam_rows),
                                           _ptr(out)))
+        return out
+
+    def unproject(self, points, Z, intrinsic, distortion, rotation_matrix, tvec):
+        points = _f64(points)
+        Zv = _f64(np.atleast_1d(Z)).ravel()
+        K, R = _f64(intrinsic, (3, 3)), _f64(rotation_matrix, (3, 3))
+        d = np.zeros(5)
+        dv = _f64(distortion).ravel()
+        d[: min(5, dv.size)] = dv[:5]
+        t = _f64(tvec).ravel()[:3].copy()
+        out = np.empty((points.shape[0], 3))
+        self._check(self.lib.lcba_unproject(self.h, points.shape[0], _ptr(points), _ptr(Zv), Zv.size,
+                                            _ptr(K), _ptr(d), _ptr(R), _ptr(t), _ptr(out)))
         return out
 
     def residuals(self, x=None, want_r=True):

@@ -159,6 +159,44 @@ k_jacobian_blocks(const double* __restrict__ tab, const double* __restrict__ pts
   }
 }
 
+// ---- 3-D initialisation: Unproject (lasercalib/rigid_body.py:205-243) --------------------
+// OpenCV's iterative undistortPoints (5 fixed-point iterations, the default TermCriteria) for
+// the (k1, k2, p1, p2, k3) model, then ray / plane z = Z intersection in world coordinates.
+// par: K row-major (9), dist (5), R row-major (9), t (3).  Z has nZ = 1 or M entries.
+__global__ void k_unproject(const double2* __restrict__ uv, const double* __restrict__ Z, int nZ,
+                            const double* __restrict__ par, long long M,
+                            double* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  const double fx = par[0], fy = par[4], cx = par[2], cy = par[5];
+  const double k1 = par[9], k2 = par[10], p1 = par[11], p2 = par[12], k3 = par[13];
+  const double* R = par + 14;
+  const double* t = par + 23;
+  const double2 p = uv[i];
+  const double x0 = (p.x - cx) / fx, y0 = (p.y - cy) / fy;
+  double x = x0, y = y0;
+  for (int it = 0; it < 5; ++it) {
+    const double r2 = x * x + y * y;
+    const double icdist = 1.0 / (1.0 + ((k3 * r2 + k2) * r2 + k1) * r2);
+    if (icdist < 0.0) { x = x0; y = y0; break; }
+    const double dx = 2.0 * p1 * x * y + p2 * (r2 + 2.0 * x * x);
+    const double dy = p1 * (r2 + 2.0 * y * y) + 2.0 * p2 * x * y;
+    x = (x0 - dx) * icdist;
+    y = (y0 - dy) * icdist;
+  }
+  // the reference maps back through P = K and normalises again: (x*fx + cx - cx)/fx
+  const double u = ((x * fx + cx) - cx) / fx, v = ((y * fy + cy) - cy) / fy;
+  // left = R^T [u v 1],  right0 = R^T t
+  const double l2 = R[2] * u + R[5] * v + R[8];
+  const double r02 = R[2] * t[0] + R[5] * t[1] + R[8] * t[2];
+  const double zw = Z[nZ == 1 ? 0 : i];
+  const double zc = (zw + r02) / l2;
+  const double a0 = u * zc - t[0], a1 = v * zc - t[1], a2 = zc - t[2];
+  out[3 * i] = R[0] * a0 + R[3] * a1 + R[6] * a2;
+  out[3 * i + 1] = R[1] * a0 + R[4] * a1 + R[7] * a2;
+  out[3 * i + 2] = R[2] * a0 + R[5] * a1 + R[8] * a2;
+}
+
 // ---- bundle_adjustment_sparsity (pySBA.py:103-118) ---------------------------------
 // 14 sorted column indices per row, rows 2i and 2i+1 identical.  One thread per entry.
 __global__ void k_sparsity_indices(const long long* __restrict__ cam_idx,

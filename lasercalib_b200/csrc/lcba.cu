@@ -489,6 +489,43 @@ extern "C" int lcba_project(lcba_t* h, int64_t M, const double* pts, const doubl
   return rows_call(h, M, pts, 3, cams_rows, NCP, out_uv, 2, 1);
 }
 
+extern "C" int lcba_unproject(lcba_t* h, int64_t M, const double* uv, const double* Z, int64_t nZ,
+                              const double* camera_matrix, const double* dist5, const double* rc_ext,
+                              const double* tc_ext, double* out_xyz) {
+  if (!h) return LCBA_E_ARG;
+  if (M < 0 || (nZ != 1 && nZ != M) || !camera_matrix || !dist5 || !rc_ext || !tc_ext ||
+      (M > 0 && (!uv || !Z || !out_xyz))) {
+    set_error(h, "lcba_unproject: bad argument (Z must have 1 or M entries)");
+    return LCBA_E_ARG;
+  }
+  if (M == 0) return LCBA_OK;
+  cudaSetDevice(h->device);
+  double par[26];
+  memcpy(par, camera_matrix, 9 * 8);
+  memcpy(par + 9, dist5, 5 * 8);
+  memcpy(par + 14, rc_ext, 9 * 8);
+  memcpy(par + 23, tc_ext, 3 * 8);
+  double *d_uv = nullptr, *d_Z = nullptr, *d_par = nullptr, *d_out = nullptr;
+  cudaError_t e = cudaMallocAsync(&d_uv, (size_t)M * 16, h->stream);
+  if (e == cudaSuccess) e = cudaMallocAsync(&d_Z, (size_t)nZ * 8, h->stream);
+  if (e == cudaSuccess) e = cudaMallocAsync(&d_par, sizeof(par), h->stream);
+  if (e == cudaSuccess) e = cudaMallocAsync(&d_out, (size_t)M * 24, h->stream);
+  if (e == cudaSuccess) {
+    cudaMemcpyAsync(d_uv, uv, (size_t)M * 16, cudaMemcpyHostToDevice, h->stream);
+    cudaMemcpyAsync(d_Z, Z, (size_t)nZ * 8, cudaMemcpyHostToDevice, h->stream);
+    cudaMemcpyAsync(d_par, par, sizeof(par), cudaMemcpyHostToDevice, h->stream);
+    k_unproject<<<nblk(M, 256), 256, 0, h->stream>>>((const double2*)d_uv, d_Z, (int)nZ, d_par, M, d_out);
+    h->launches++;
+    cudaMemcpyAsync(out_xyz, d_out, (size_t)M * 24, cudaMemcpyDeviceToHost, h->stream);
+    e = cudaStreamSynchronize(h->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+  }
+  void* tmp[] = {d_uv, d_Z, d_par, d_out};
+  for (void* q : tmp) if (q) cudaFreeAsync(q, h->stream);
+  if (e != cudaSuccess) { set_error(h, std::string("lcba_unproject: ") + cudaGetErrorString(e)); return LCBA_E_CUDA; }
+  return LCBA_OK;
+}
+
 extern "C" int lcba_sparsity_indices(lcba_t* h, int32_t C, int64_t P, int64_t N, const int64_t* cam_idx,
                                      const int64_t* pt_idx, int32_t* indices_out) {
   if (!h) return LCBA_E_ARG;

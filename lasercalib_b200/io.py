@@ -64,3 +64,16 @@ def camera_vector_from_calibration(camera_matrix, distortion, rc_ext, tc_ext):
     v[6:9] = [camera_matrix[0][0], d[0], d[1]]
     v[9:11] = [camera_matrix[0][2], camera_matrix[1][2]]
     return v
+
+
+def Unproject(points, Z, intrinsic, distortion, rotation_matrix, tvec, engine=None):
+    """Pixels of one camera -> world points on the plane(s) z = Z, on the GPU
+    (``lasercalib/rigid_body.py:205-243``: OpenCV undistortPoints + ray/plane intersection;
+    same name and argument order as the reference).  ``Z``: one number or [num_pts]."""
+    from . import _cabi
+    eng = engine or _cabi.Engine()
+    try:
+        return eng.unproject(points, Z, intrinsic, distortion, rotation_matrix, tvec)
+    finally:
+        if engine is None:
+            eng.close()

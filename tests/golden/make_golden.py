@@ -227,12 +227,38 @@ def golden_io():
                         tc_ext=np.array([r[3] for r in raw]), **VERS)
 
 
+def golden_unproject():
+    """lasercalib/rigid_body.py:205-243 Unproject on three example cameras (+ a strongly
+    distorted variant with tangential terms and k3)."""
+    from lasercalib.rigid_body import Unproject
+    g = np.load(os.path.join(HERE, "io_example17.npz"))
+    rng = np.random.default_rng(5)
+    outs, pts_all, Zs = [], [], []
+    for i in (0, 8, 16):
+        pts = np.column_stack([rng.uniform(0, 3208, 200), rng.uniform(0, 2200, 200)])
+        Z = rng.choice([0.0, 106.0], 200)
+        outs.append(Unproject(pts, Z, g["camera_matrix"][i], g["distortion"][i], g["rc_ext"][i],
+                              g["tc_ext"][i]))
+        pts_all.append(pts)
+        Zs.append(Z)
+    d2 = np.array([[-0.1], [0.02], [1e-3], [-5e-4], [3e-3]])
+    pts = np.column_stack([rng.uniform(0, 3208, 200), rng.uniform(0, 2200, 200)])
+    out2 = Unproject(pts, [106.0], g["camera_matrix"][0], d2, g["rc_ext"][0], g["tc_ext"][0])
+    np.savez_compressed(os.path.join(HERE, "unproject_example.npz"), cam_ids=np.array([0, 8, 16]),
+                        pts=np.array(pts_all), Z=np.array(Zs), out=np.array(outs), d2=d2, pts2=pts,
+                        out2=out2, **VERS)
+
+
 if __name__ == "__main__":
+    if "--only-unproject" in sys.argv:
+        golden_unproject()
+        sys.exit(0)
     if "--only-sharedcam" in sys.argv:
         golden_sharedcam()
         sys.exit(0)
     if "--only-io" in sys.argv:
         golden_io()
+    golden_unproject()
         sys.exit(0)
     if "--only-nocam" in sys.argv:
         golden_nocam()

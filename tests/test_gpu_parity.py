@@ -360,6 +360,21 @@ def test_bundleAdjust_sharedcam(PySBA, golden):
     np.testing.assert_allclose(res2.cost, float(g["ref_cost"]), rtol=2e-3)
 
 
+def test_unproject_matches_reference(golden):
+    """rigid_body.Unproject (OpenCV undistortPoints + ray/plane) on the GPU."""
+    from lasercalib_b200.io import Unproject
+    g, cal = golden("unproject_example"), golden("io_example17")
+    for n, i in enumerate(g["cam_ids"]):
+        out = Unproject(g["pts"][n], g["Z"][n], cal["camera_matrix"][i], cal["distortion"][i],
+                        cal["rc_ext"][i], cal["tc_ext"][i])
+        np.testing.assert_allclose(out, g["out"][n], rtol=0, atol=1e-8)      # mm
+    out2 = Unproject(g["pts2"], [106.0], cal["camera_matrix"][0], g["d2"], cal["rc_ext"][0],
+                     cal["tc_ext"][0])
+    np.testing.assert_allclose(out2, g["out2"], rtol=0, atol=1e-8)
+    assert Unproject(np.zeros((0, 2)), [0.0], cal["camera_matrix"][0], g["d2"], cal["rc_ext"][0],
+                     cal["tc_ext"][0]).shape == (0, 3)
+
+
 # ----------------------------------------------------------------------------- error paths
 def test_error_behaviour(PySBA, Engine):
     from lasercalib_b200._cabi import LcbaError
