@@ -250,18 +250,12 @@ def golden_unproject():
 
 
 if __name__ == "__main__":
-    if "--only-unproject" in sys.argv:
-        golden_unproject()
-        sys.exit(0)
-    if "--only-sharedcam" in sys.argv:
-        golden_sharedcam()
-        sys.exit(0)
-    if "--only-io" in sys.argv:
-        golden_io()
-    golden_unproject()
-        sys.exit(0)
-    if "--only-nocam" in sys.argv:
-        golden_nocam()
+    only = {"--only-unproject": golden_unproject, "--only-sharedcam": golden_sharedcam,
+            "--only-io": golden_io, "--only-nocam": golden_nocam}
+    picked = [fn for flag, fn in only.items() if flag in sys.argv]
+    if picked:
+        for fn in picked:
+            fn()
         sys.exit(0)
     golden_nocam()
     golden_sharedcam()
@@ -271,3 +265,4 @@ if __name__ == "__main__":
     golden_ba("ba_ring8_volume1500", "ring8", 1500, "volume")
     golden_ba("ba_example18_vis60_800", "example18", 800, "volume", p_vis=0.6)
     golden_io()
+    golden_unproject()
