@@ -212,7 +212,8 @@ def main():
 
     # ---- device-resident run (value) ----
     eng = Engine(local)
-    eng.set_problem(pb["cams0"], sh["pts"], sh["points_2d"], sh["camera_ind"], sh["point_ind"])
+    eng.set_problem(pb["cams0"], sh["pts"], sh["points_2d"], sh["camera_ind"], sh["point_ind"],
+                    pt_offset=sh["pt_offset"])
     if ws > 1:
         D.connect_engine(eng)
     # Exactly K outer iterations of the real trajectory: bundleAdjust(1e-4) from the standard
@@ -267,7 +268,7 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", HBM_FALLBACK_GBS))
     fp64_peak = FP64_PEAK_FALLBACK_TFLOPS
     n_loc, p_loc = sh["point_ind"].size, sh["pts"].shape[0]
-    k_loc = np.bincount(np.bincount(sh["point_ind"], minlength=p_loc))
+    k_loc = np.bincount(np.bincount(sh["point_ind"] - sh["pt_offset"], minlength=p_loc))
     roof = None
     if "schur" in prof:
         ms_schur = prof["schur"]["total_ms"] / prof["schur"]["launches"]

@@ -127,6 +127,11 @@ void lcba_default_options(lcba_options* o);
 int lcba_set_problem(lcba_t* h, int32_t C, int64_t P, int64_t N, const double* cams,
                      const double* pts, const double* obs_uv, const int64_t* cam_idx,
                      const int64_t* pt_idx, const double* weights_or_null);
+/* Same for one shard of a point-sharded job: pts holds the shard's P points, pt_idx may keep the
+ * caller's GLOBAL point indices, pt_offset = global index of the shard's first point. */
+int lcba_set_problem_shard(lcba_t* h, int32_t C, int64_t P, int64_t N, const double* cams,
+                           const double* pts, const double* obs_uv, const int64_t* cam_idx,
+                           const int64_t* pt_idx, const double* weights_or_null, int64_t pt_offset);
 /* Replace the current parameter vector x = [cams.ravel(), pts.ravel()]. */
 int lcba_set_params(lcba_t* h, const double* cams, const double* pts);
 /* PySBA.optimizedParams (pySBA.py:121-129): copy x back, split. */

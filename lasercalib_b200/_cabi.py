@@ -16,7 +16,7 @@ E_NAMES = {-1: "LCBA_E_ARG", -2: "LCBA_E_CUDA", -3: "LCBA_E_STATE", -4: "LCBA_E_
 
 # every symbol include/lcba.h declares (tests/test_cabi.py checks the export list)
 SYMBOLS = ["lcba_version", "lcba_create", "lcba_destroy", "lcba_last_error", "lcba_default_options",
-           "lcba_set_problem", "lcba_set_params", "lcba_get_params", "lcba_rotate", "lcba_project",
+           "lcba_set_problem", "lcba_set_problem_shard", "lcba_set_params", "lcba_get_params", "lcba_rotate", "lcba_project",
            "lcba_unproject", "lcba_residuals", "lcba_jacobian_blocks", "lcba_sparsity_indices", "lcba_solve",
            "lcba_get_trace", "lcba_get_grad", "lcba_get_profile", "lcba_linearize",
            "lcba_time_device", "lcba_nccl_unique_id", "lcba_comm_init", "lcba_debug_tr2d"]
@@ -75,6 +75,7 @@ def load():
     lib.lcba_default_options.argtypes = [C.POINTER(Options)]
     lib.lcba_default_options.restype = None
     lib.lcba_set_problem.argtypes = [vp, i32, i64, i64, vp, vp, vp, vp, vp, vp]
+    lib.lcba_set_problem_shard.argtypes = [vp, i32, i64, i64, vp, vp, vp, vp, vp, vp, i64]
     lib.lcba_set_params.argtypes = [vp, vp, vp]
     lib.lcba_get_params.argtypes = [vp, vp, vp]
     lib.lcba_rotate.argtypes = [vp, i64, vp, vp, vp]
@@ -139,7 +140,7 @@ class Engine:
             raise LcbaError(rc, self.lib.lcba_last_error(self.h).decode())
 
     # ---- problem ----
-    def set_problem(self, cams, pts, points_2d, camera_ind, point_ind, weights=None):
+    def set_problem(self, cams, pts, points_2d, camera_ind, point_ind, weights=None, pt_offset=0):
         cams, pts = _f64(cams), _f64(pts)
         p2 = _f64(points_2d)
         ci, pi = _i64(camera_ind).ravel(), _i64(point_ind).ravel()
@@ -151,8 +152,9 @@ class Engine:
         N = ci.size
         if pi.size != N or p2.shape != (N, 2) or (w is not None and w.size != N):
             raise ValueError("observation arrays must share their first dimension")
-        self._check(self.lib.lcba_set_problem(self.h, cams.shape[0], pts.shape[0], N, _ptr(cams),
-                                              _ptr(pts), _ptr(p2), _ptr(ci), _ptr(pi), _ptr(w)))
+        self._check(self.lib.lcba_set_problem_shard(self.h, cams.shape[0], pts.shape[0], N,
+                                                    _ptr(cams), _ptr(pts), _ptr(p2), _ptr(ci),
+                                                    _ptr(pi), _ptr(w), int(pt_offset)))
         self.C, self.P, self.N = cams.shape[0], pts.shape[0], N
 
     def set_params(self, cams, pts):

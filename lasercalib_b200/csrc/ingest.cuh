@@ -8,12 +8,14 @@
 namespace lcba {
 
 // flags[0] |= 1 index out of range ; |= 2 not sorted by (pt, cam)
+// pt_off: first point of this shard (the caller may pass global point indices)
 __global__ void k_make_keys(const long long* __restrict__ cam_idx,
                             const long long* __restrict__ pt_idx, long long N, int C, long long P,
-                            unsigned long long* __restrict__ keys, int* __restrict__ flags) {
+                            long long pt_off, unsigned long long* __restrict__ keys,
+                            int* __restrict__ flags) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
-  const long long c = cam_idx[i], p = pt_idx[i];
+  const long long c = cam_idx[i], p = pt_idx[i] - pt_off;
   if (c < 0 || c >= C || p < 0 || p >= P) {
     atomicOr(flags, 1);
     keys[i] = 0;
@@ -22,7 +24,7 @@ __global__ void k_make_keys(const long long* __restrict__ cam_idx,
   const unsigned long long k = ((unsigned long long)p << 8) | (unsigned long long)c;
   keys[i] = k;
   if (i > 0) {
-    const long long c0 = cam_idx[i - 1], p0 = pt_idx[i - 1];
+    const long long c0 = cam_idx[i - 1], p0 = pt_idx[i - 1] - pt_off;
     if (p0 > p || (p0 == p && c0 > c)) atomicOr(flags, 2);
   }
 }

@@ -267,6 +267,12 @@ static inline unsigned nblk(long long n, int t) { return (unsigned)std::max<long
 extern "C" int lcba_set_problem(lcba_t* h, int32_t C, int64_t P, int64_t N, const double* cams,
                                 const double* pts, const double* obs_uv, const int64_t* cam_idx,
                                 const int64_t* pt_idx, const double* weights) {
+  return lcba_set_problem_shard(h, C, P, N, cams, pts, obs_uv, cam_idx, pt_idx, weights, 0);
+}
+
+extern "C" int lcba_set_problem_shard(lcba_t* h, int32_t C, int64_t P, int64_t N, const double* cams,
+                                      const double* pts, const double* obs_uv, const int64_t* cam_idx,
+                                      const int64_t* pt_idx, const double* weights, int64_t pt_offset) {
   if (!h) return LCBA_E_ARG;
   if (C <= 0 || P <= 0 || N <= 0 || !cams || !pts || !obs_uv || !cam_idx || !pt_idx) {
     set_error(h, "lcba_set_problem: null pointer or non-positive size");
@@ -334,7 +340,7 @@ extern "C" int lcba_set_problem(lcba_t* h, int32_t C, int64_t P, int64_t N, cons
   if (weights) ING(cudaMemcpyAsync(t_w, weights, N * 8, cudaMemcpyHostToDevice, st));
   ING(cudaMemcpyAsync(h->d_cams[0], cams, (size_t)C * NCP * 8, cudaMemcpyHostToDevice, st));
   ING(cudaMemcpyAsync(h->d_pts[0], pts, (size_t)P * 3 * 8, cudaMemcpyHostToDevice, st));
-  k_make_keys<<<nblk(N, 256), 256, 0, st>>>(t_cam, t_pt, N, C, P, t_keys, d_flags);
+  k_make_keys<<<nblk(N, 256), 256, 0, st>>>(t_cam, t_pt, N, C, P, pt_offset, t_keys, d_flags);
   h->launches++;
   int flags[2] = {0, 0};
   ING(cudaMemcpyAsync(flags, d_flags, sizeof(int), cudaMemcpyDeviceToHost, st));

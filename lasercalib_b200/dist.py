@@ -75,8 +75,9 @@ def _is_point_major(point_ind):
 def shard_problem(points3D, points2D, camera_ind, point_ind, weights, rank, nranks, bounds=None):
     """This rank's slice: points [lo, hi), the observations that reference them (local point
     indices), all cameras implied.  Returns dict(pts, points_2d, camera_ind, point_ind,
-    weights, lo, hi, obs_sel); obs_sel indexes the caller's observation arrays (a slice for
-    point-major input, an index array otherwise)."""
+    weights, lo, hi, obs_sel, pt_offset); obs_sel indexes the caller's observation arrays (a
+    slice for point-major input, an index array otherwise); local point index =
+    point_ind - pt_offset (point-major input keeps views of the caller's arrays: no copies)."""
     point_ind = np.asarray(point_ind)
     P = points3D.shape[0]
     N = point_ind.size
@@ -95,7 +96,7 @@ def shard_problem(points3D, points2D, camera_ind, point_ind, weights, rank, nran
         return dict(pts=np.ascontiguousarray(points3D[lo:hi]),
                     points_2d=np.asarray(points2D)[o0:o1],
                     camera_ind=np.asarray(camera_ind)[o0:o1],
-                    point_ind=point_ind[o0:o1] - lo,
+                    point_ind=point_ind[o0:o1], pt_offset=lo,     # global indices + offset
                     weights=w, lo=lo, hi=hi, obs_sel=slice(o0, o1), bounds=b)
     if bounds is None:
         bounds = shard_bounds(point_ind, P, nranks)
@@ -105,7 +106,7 @@ def shard_problem(points3D, points2D, camera_ind, point_ind, weights, rank, nran
     return dict(pts=np.ascontiguousarray(points3D[lo:hi]),
                 points_2d=np.ascontiguousarray(np.asarray(points2D)[sel]),
                 camera_ind=np.ascontiguousarray(np.asarray(camera_ind)[sel]),
-                point_ind=np.ascontiguousarray(point_ind[sel] - lo),
+                point_ind=np.ascontiguousarray(point_ind[sel] - lo), pt_offset=0,
                 weights=w, lo=lo, hi=hi, obs_sel=sel, bounds=bounds)
 
 

@@ -33,6 +33,9 @@ TERMINATION_MESSAGES = {
 }
 
 
+_ENGINES = {}      # device -> shared _cabi.Engine
+
+
 class BAResult(OptimizeResult):
     """OptimizeResult whose large members (``fun``, ``jac``) are produced on first access
     (the reference materialises a 2N x n CSR Jacobian: ~4 KB per observation)."""
@@ -96,6 +99,7 @@ class PySBA:
         self.points3Dfixed_labeled = None
         self._engine = None
         self._problem_key = None
+        self._fresh_problem = True
         self.last_trace = None
 
     @property
@@ -114,6 +118,7 @@ class PySBA:
         d = dict(self.__dict__)
         d["_engine"] = None
         d["_problem_key"] = None
+        d.pop("_keep", None)
         return d
 
     def __setstate__(self, d):
@@ -121,10 +126,18 @@ class PySBA:
 
     # ---- engine plumbing ----
     def _get_engine(self):
+        """One engine (GPU handle, stream, NCCL attachment) per device and process, shared by
+        all PySBA objects; `_owner` tells whose observation set is resident."""
         if self._engine is None:
             rank, ws, local = _dist.world()
-            self._engine = _cabi.Engine(local if ws > 1 else -1)
-            self._comm_ready = False
+            dev = local if ws > 1 else -1
+            eng = _ENGINES.get(dev)
+            if eng is None or eng.h is None:
+                eng = _cabi.Engine(dev)
+                eng._comm_ready = False
+                eng._owner = None
+                _ENGINES[dev] = eng
+            self._engine = eng
         return self._engine
 
     def _weights_arg(self, pointWeights):
@@ -146,9 +159,10 @@ class PySBA:
         p2 = np.asarray(points_2d)
         key = (cams.shape[0], pts.shape[0], ci.ctypes.data, ci.size, pi.ctypes.data,
                p2.ctypes.data, wkey)
-        self._fresh_problem = key != self._problem_key
+        self._fresh_problem = key != self._problem_key or eng._owner is not self
         if self._fresh_problem:
             eng.set_problem(cams, pts, p2, ci, pi, w)
+            eng._owner = self
             self._problem_key = key
             self._keep = (ci, pi, p2, w)       # keep the keyed buffers alive
         return eng
@@ -220,11 +234,12 @@ class PySBA:
                                         self.point2DIndices, w, rank, ws)
             eng = self._get_engine()
             eng.set_problem(cams0, shard["pts"], shard["points_2d"], shard["camera_ind"],
-                            shard["point_ind"], shard["weights"])
+                            shard["point_ind"], shard["weights"], pt_offset=shard["pt_offset"])
             self._problem_key = None
-            if not self._comm_ready:
+            eng._owner = self
+            if not eng._comm_ready:
                 _dist.connect_engine(eng)
-                self._comm_ready = True
+                eng._comm_ready = True
             if verbose and rank != 0:
                 verbose = 0
         else:

@@ -34,6 +34,7 @@ def main():
     # ---- this rank's shard ----
     sh = D.shard_problem(pb["pts0"], pb["points_2d"], ci, pi, None, rank, ws)
     b = sh["bounds"]
+    sh["point_ind"] = sh["point_ind"] - sh["pt_offset"]        # local indices for the oracle
     assert b[0] == 0 and b[-1] == P and np.all(np.diff(b) >= 0)
     Pl = sh["pts"].shape[0]
     wl = O.default_weights(sh["point_ind"])

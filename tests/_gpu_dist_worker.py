@@ -31,7 +31,8 @@ def main():
     # sharded: reduced camera system
     sh = D.shard_problem(pb["pts0"], pb["points_2d"], pb["camera_ind"], pb["point_ind"], None, rank, ws)
     e2 = Engine(local)
-    e2.set_problem(pb["cams0"], sh["pts"], sh["points_2d"], sh["camera_ind"], sh["point_ind"])
+    e2.set_problem(pb["cams0"], sh["pts"], sh["points_2d"], sh["camera_ind"], sh["point_ind"],
+                   pt_offset=sh["pt_offset"])
     D.connect_engine(e2)
     lin2 = e2.linearize(1e-6)
     assert np.abs(lin2["S"] - lin1["S"]).max() <= 1e-12 * np.abs(lin1["S"]).max()
