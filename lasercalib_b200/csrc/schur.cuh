@@ -300,7 +300,7 @@ k_schur(const double* __restrict__ tab, const double* __restrict__ pts,
   // per stage: Y[SP][nslots][Y_LD] J[SP][ndiag][JC_LD] mask[SP] pad[SP] (even => 16 B)
   const size_t stage_doubles = (size_t)SP * nslots * Y_LD + (size_t)SP * ndiag * JC_LD + SP * 2;
   double* s_tab = s_dyn + SCHUR_STAGES * stage_doubles;      // C * CAMTAB
-  enum { BAR_FULL = 2, BAR_EMPTY = 4, BAR_PROD = 6 };
+  enum { BAR_FULL = 2, BAR_EMPTY = BAR_FULL + SCHUR_STAGES, BAR_PROD = BAR_EMPTY + SCHUR_STAGES };
 
   // slice boundaries balanced by observation count
   const int slice = blockIdx.x;
