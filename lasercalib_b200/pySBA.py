@@ -150,6 +150,16 @@ class PySBA:
         wf = np.ascontiguousarray(w, dtype=np.float64)
         return wf, ("w", wf.ctypes.data, wf.size, float(wf[:8].sum()))
 
+    @staticmethod
+    def _fingerprint(a):
+        """Cheap content signature (64 strided samples + their sum) so that an observation
+        array edited in place is re-uploaded instead of served from the resident copy."""
+        flat = a.reshape(-1)
+        if flat.size == 0:
+            return (0,)
+        smp = flat[:: max(1, flat.size // 64)][:64]
+        return (flat.size, float(smp.sum()), float(flat[-1]))
+
     def _ensure_problem(self, cams, pts, camera_indices, point_indices, points_2d, pointWeights):
         """(Re)load the observation set on the device unless it is already resident."""
         eng = self._get_engine()
@@ -158,7 +168,8 @@ class PySBA:
         pi = np.asarray(point_indices)
         p2 = np.asarray(points_2d)
         key = (cams.shape[0], pts.shape[0], ci.ctypes.data, ci.size, pi.ctypes.data,
-               p2.ctypes.data, wkey)
+               p2.ctypes.data, wkey, self._fingerprint(ci), self._fingerprint(pi),
+               self._fingerprint(p2))
         self._fresh_problem = key != self._problem_key or eng._owner is not self
         if self._fresh_problem:
             eng.set_problem(cams, pts, p2, ci, pi, w)

@@ -75,6 +75,18 @@ def test_fun_matches_reference(PySBA, golden):
     np.testing.assert_allclose(f1, ref1, rtol=0, atol=1e-8)
 
 
+def test_fun_sees_in_place_edits_of_the_observations(PySBA):
+    pb = make_rig("ring4", 200, seed=1)
+    C, P = pb["n_cams"], pb["n_points"]
+    p2 = pb["points_2d"].copy()
+    sba = PySBA(pb["cams0"], pb["pts0"], p2, pb["camera_ind"], pb["point_ind"])
+    x0 = np.hstack((pb["cams0"].ravel(), pb["pts0"].ravel()))
+    f0 = sba.fun(x0, C, P, pb["camera_ind"], pb["point_ind"], p2, sba.pointWeights)
+    p2 += 1.0                                        # same buffer, new content
+    f1 = sba.fun(x0, C, P, pb["camera_ind"], pb["point_ind"], p2, sba.pointWeights)
+    np.testing.assert_allclose(f1, f0 - 1.0, atol=1e-9)
+
+
 def test_fun_on_shuffled_observations(PySBA):
     pb = make_rig("example18", 600, seed=3, variant="volume", p_vis=0.7)
     sh = shuffle_observations(pb, seed=5)
