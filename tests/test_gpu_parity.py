@@ -211,6 +211,25 @@ def test_trajectory_matches_exact_trf_oracle(Engine, golden, name):
     assert rel.max() < 1e-6, rel                                  # intrinsics, relative
 
 
+@pytest.mark.parametrize("rig,npts,pvis,variant", [("wide8", 400, 1.0, "volume"),      # config 4 geometry
+                                                   ("ring64", 150, 0.5, "volume"),     # config 5 geometry
+                                                   ("ring24", 300, 0.6, "planar"),     # two-plane points
+                                                   ("ring4", 2500, 1.0, "volume")])    # config 1 geometry
+def test_trajectory_matches_oracle_on_baseline_rigs(Engine, rig, npts, pvis, variant):
+    """BASELINE.json configs 1/3/4/5 geometries at oracle-sized point counts."""
+    pb = make_rig(rig, npts, seed=21, variant=variant, p_vis=pvis)
+    ora = O.trf_exact(pb["cams0"], pb["pts0"], pb["points_2d"], pb["camera_ind"], pb["point_ind"],
+                      ftol=1e-4)
+    eng = Engine()
+    eng.set_problem(pb["cams0"], pb["pts0"], pb["points_2d"], pb["camera_ind"], pb["point_ind"])
+    res, trace = eng.solve(ftol=1e-4)
+    f, _ = eng.residuals()
+    eng.close()
+    assert res.nfev == ora.nfev and res.status == ora.status
+    np.testing.assert_allclose(res.cost, ora.cost, rtol=1e-8)
+    assert abs(O.rmse_px(f) - O.rmse_px(ora.fun)) < 1e-6
+
+
 def test_first_step_and_final_rmse_vs_tight_scipy(Engine, golden):
     """P3: one step from the common x0 against scipy with tight LSMR; P4: final RMSE."""
     g = golden("ba_ring8_volume1500")
