@@ -85,6 +85,7 @@ struct lcba_handle {
   double *d_campart = nullptr, *d_part = nullptr, *d_red = nullptr, *d_coef = nullptr;
   double *d_S = nullptr, *d_Lf = nullptr, *d_rhs = nullptr, *d_Sred = nullptr, *d_Spart = nullptr;
   int* d_fail = nullptr;
+  long long* d_stats = nullptr;   // LCBA_SCHUR_STATS=1: per-CTA cycle counters of k_schur
   Ctl* d_ctl = nullptr;
   Ctl* h_ctl = nullptr;   // pinned
   int lin_grid = 0, obs_grid = 0, pt_grid = 0;
@@ -432,6 +433,8 @@ extern "C" int lcba_set_problem_shard(lcba_t* h, int32_t C, int64_t P, int64_t N
                                cudaMemcpyHostToDevice, st));
   LCBA_TRY(dev_alloc(h, &h->d_Sred, h->plan.part_stride));
   LCBA_TRY(dev_alloc(h, &h->d_Spart, h->plan.part_stride * h->plan.nslices));
+  h->d_stats = nullptr;
+  if (getenv("LCBA_SCHUR_STATS")) LCBA_TRY(dev_alloc(h, &h->d_stats, (size_t)h->plan.nslices * h->plan.nkinds * 4));
   LCBA_CUDA(h, cudaStreamSynchronize(st));
   h->have_problem = true;
   return LCBA_OK;
@@ -690,7 +693,7 @@ static int pass_schur(lcba_t* h, const double* lam_host_or_null) {
 #define LCBA_SCHUR_LAUNCH(SK, NR)                                                                   \
   KL(h, "schur", (k_schur<SK, NR><<<grid, pl.max_threads, pl.smem_bytes, h->stream>>>(              \
         h->d_tab[w], h->d_pts[w], h->d_w, h->d_obs_start, h->d_mask, h->d_Lz, h->P, h->N, C,        \
-        h->d_kinds, h->d_hws, pl.nslices, pl.part_stride, pl.npairs, h->d_Spart)))
+        h->d_kinds, h->d_hws, pl.nslices, pl.part_stride, pl.npairs, h->d_Spart, h->d_stats)))
   if (pl.cfg != 1) { if (skip) LCBA_SCHUR_LAUNCH(true, 160); else LCBA_SCHUR_LAUNCH(false, 160); }
   else             { if (skip) LCBA_SCHUR_LAUNCH(true, 128); else LCBA_SCHUR_LAUNCH(false, 128); }
 #undef LCBA_SCHUR_LAUNCH
@@ -1139,6 +1142,16 @@ extern "C" int lcba_comm_init(lcba_t* h, int32_t rank, int32_t nranks, const voi
   h->comm = comm;
   h->rank = rank;
   h->nranks = nranks;
+  return LCBA_OK;
+}
+
+// debug: per-CTA cycle counters of the last k_schur launch (LCBA_SCHUR_STATS=1)
+extern "C" int lcba_debug_schur_stats(lcba_t* h, long long* out, int max_ctas, int* nkinds, int* nslices) {
+  if (!h || !h->d_stats || !out) return LCBA_E_STATE;
+  const int n = std::min(max_ctas, h->plan.nslices * h->plan.nkinds);
+  cudaMemcpy(out, h->d_stats, (size_t)n * 4 * sizeof(long long), cudaMemcpyDeviceToHost);
+  *nkinds = h->plan.nkinds;
+  *nslices = h->plan.nslices;
   return LCBA_OK;
 }
 

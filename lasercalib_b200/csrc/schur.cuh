@@ -290,9 +290,12 @@ k_schur(const double* __restrict__ tab, const double* __restrict__ pts,
         const double* __restrict__ wgt, const uint32_t* __restrict__ obs_start,
         const unsigned long long* __restrict__ mask, const double* __restrict__ Lz, long long P,
         long long N, int C, const SchurKind* __restrict__ kinds, const SchurHw* __restrict__ hws,
-        int nslices, size_t part_stride, int npairs, double* __restrict__ part) {
+        int nslices, size_t part_stride, int npairs, double* __restrict__ part,
+        long long* __restrict__ stats) {
   extern __shared__ __align__(16) double s_dyn[];
   const SchurKind& K = kinds[blockIdx.y];
+  const long long t_start = clock64();
+  long long t_wait = 0;
   const int nthreads = K.threads;
   const int tid = threadIdx.x;
   if (tid >= nthreads) return;          // uniform per warp (threads multiple of 32)
@@ -320,7 +323,7 @@ k_schur(const double* __restrict__ tab, const double* __restrict__ pts,
     nbar_sync(BAR_PROD, nprod);
     for (long long c = 0; c < nchunks + SCHUR_STAGES; ++c) {
       const int st = (int)(c % SCHUR_STAGES);
-      if (c >= SCHUR_STAGES) nbar_sync(BAR_EMPTY + st, nthreads);
+      if (c >= SCHUR_STAGES) { const long long t0 = clock64(); nbar_sync(BAR_EMPTY + st, nthreads); t_wait += clock64() - t0; }
       if (c >= nchunks) continue;
       double* s_Y = s_dyn + st * stage_doubles;
       double* s_J = s_Y + (size_t)SP * nslots * Y_LD;
@@ -353,6 +356,11 @@ k_schur(const double* __restrict__ tab, const double* __restrict__ pts,
       __threadfence_block();
       nbar_arrive(BAR_FULL + st, nthreads);
     }
+    if (stats && tid == prod0) {
+      long long* o = stats + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 4;
+      o[2] = t_wait;
+      o[3] = clock64() - t_start;
+    }
     return;
   }
 
@@ -383,7 +391,7 @@ k_schur(const double* __restrict__ tab, const double* __restrict__ pts,
     const unsigned long long* s_mask =
         reinterpret_cast<const unsigned long long*>(s_J + (size_t)SP * ndiag * JC_LD);
     const int npc = (int)min((long long)SP, pb - (pa + c * SP));
-    nbar_sync(BAR_FULL + st, nthreads);
+    { const long long t0 = clock64(); nbar_sync(BAR_FULL + st, nthreads); t_wait += clock64() - t0; }
     if (valid) {
       const double* Yq = s_Y;
       for (int q = 0; q < npc; ++q, Yq += nslots * Y_LD) {
@@ -398,10 +406,35 @@ k_schur(const double* __restrict__ tab, const double* __restrict__ pts,
           ld3(Yq + oj1 + k * 16, a1);
           ld3(Yq + ok0 + k * 16, b0);
           ld3(Yq + ok1 + k * 16, b1);
-          outer9<true>(acc[0], a0, b0);
-          if (!dwarp) outer9<true>(acc[1], a0, b1);
-          outer9<true>(acc[2], a1, b0);
-          outer9<true>(acc[3], a1, b1);
+          // DFMA issue order chosen for register-operand reuse: a DFMA with three fresh
+          // 64-bit register operands issues every 3 cycles on B200, every 2 with one operand
+          // held in the reuse cache (tools/fp64_operands.cu: 24.7 vs 34.1 TFLOP/s).  Six
+          // consecutive products share a[i]; the sweep direction over b alternates so that the
+          // first product of a row group reuses the last b of the previous one.
+          if (!dwarp) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+#pragma unroll
+              for (int jj = 0; jj < 6; ++jj) {
+                const int j6 = (i & 1) ? 5 - jj : jj;
+                const int j = j6 % 3;
+                if (j6 < 3) acc[0][3 * i + j] = fma(-a0[i], b0[j], acc[0][3 * i + j]);
+                else        acc[1][3 * i + j] = fma(-a0[i], b1[j], acc[1][3 * i + j]);
+              }
+            }
+          } else {
+            outer9<true>(acc[0], a0, b0);
+          }
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+#pragma unroll
+            for (int jj = 0; jj < 6; ++jj) {
+              const int j6 = (i & 1) ? jj : 5 - jj;
+              const int j = j6 % 3;
+              if (j6 < 3) acc[2][3 * i + j] = fma(-a1[i], b0[j], acc[2][3 * i + j]);
+              else        acc[3][3 * i + j] = fma(-a1[i], b1[j], acc[3][3 * i + j]);
+            }
+          }
         }
         if (dwarp) {   // U_j = sum Jc^T Jc on the diagonal pairs
           const double* Jq = s_J + (size_t)q * ndiag * JC_LD;
@@ -419,6 +452,11 @@ k_schur(const double* __restrict__ tab, const double* __restrict__ pts,
       }
     }
     nbar_arrive(BAR_EMPTY + st, nthreads);
+  }
+  if (stats && tid == 0) {
+    long long* o = stats + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 4;
+    o[0] = t_wait;
+    o[1] = clock64() - t_start;
   }
   // ---------------- write the slice partial (every lower-triangle entry exactly once) ----
   if (valid) {
