@@ -71,3 +71,36 @@ def test_shard_bounds_properties():
 
 def test_world_defaults_to_single_process():
     assert D.world() == (0, 1, 0)
+
+
+def test_shard_problem_properties_hypothesis():
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.integers(1, 60), st.integers(1, 9), st.integers(0, 2**31 - 1), st.booleans())
+    def check(P, ws, seed, shuffle):
+        rng = np.random.default_rng(seed)
+        counts = rng.integers(0, 6, P)
+        pi = np.repeat(np.arange(P), counts)
+        if pi.size == 0:
+            pi = np.array([0])
+        ci = rng.integers(0, 5, pi.size)
+        uv = rng.normal(size=(pi.size, 2))
+        if shuffle:
+            perm = rng.permutation(pi.size)
+            pi, ci, uv = pi[perm], ci[perm], uv[perm]
+        pts = rng.normal(size=(P, 3))
+        seen = np.zeros(pi.size, dtype=int)
+        covered = np.zeros(P, dtype=int)
+        for r in range(ws):
+            sh = D.shard_problem(pts, uv, ci, pi, None, r, ws)
+            local = sh["point_ind"] - sh["pt_offset"]
+            assert sh["pts"].shape[0] == sh["hi"] - sh["lo"]
+            assert local.size == 0 or (local.min() >= 0 and local.max() < sh["pts"].shape[0])
+            np.testing.assert_array_equal(pi[sh["obs_sel"]], local + sh["lo"])
+            np.testing.assert_array_equal(uv[sh["obs_sel"]], sh["points_2d"])
+            seen[sh["obs_sel"]] += 1
+            covered[sh["lo"]:sh["hi"]] += 1
+        assert np.all(seen == 1) and np.all(covered == 1)
+
+    check()

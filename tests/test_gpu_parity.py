@@ -406,6 +406,49 @@ def test_unproject_matches_reference(golden):
                      cal["tc_ext"][0]).shape == (0, 3)
 
 
+def test_calibrate_camera_script_flow(PySBA, golden):
+    """The sequence of scripts/calibrate_camera.py:32-99 around the path: two laser datasets
+    -> concatenation -> cameras from the example calibration files -> PySBA -> bundleAdjust ->
+    readable / red export -> pickle of the object."""
+    from lasercalib_b200 import io as lio
+    cal = golden("io_example17")
+    C = cal["cams"].shape[0]
+    cams_gt = np.array([lio.camera_vector_from_calibration(cal["camera_matrix"][i], cal["distortion"][i],
+                                                           cal["rc_ext"][i], cal["tc_ext"][i])
+                        for i in range(C)])
+    np.testing.assert_allclose(cams_gt[:, 3:], cal["cams"][:, 3:], atol=0)
+    rng = np.random.default_rng(4)
+    datasets = []
+    for z in (0.0, 106.0):                                   # example/config.json z_gt
+        n = 300
+        pts = np.column_stack([rng.uniform(-600, 600, n), rng.uniform(-600, 600, n), np.full(n, z)])
+        uv = O.project(np.repeat(pts, C, axis=0), np.tile(cams_gt, (n, 1))).reshape(n, C, 2)
+        vis = (uv[..., 0] > 0) & (uv[..., 0] < 3208) & (uv[..., 1] > 0) & (uv[..., 1] < 2200)
+        vis &= rng.random((n, C)) < 0.8
+        keep = (vis.sum(axis=1) >= 4) & vis[:, 0]
+        pts, uv, vis = pts[keep], uv[keep], vis[keep]
+        pi, ci = np.nonzero(vis)
+        datasets.append(dict(n_cams=C, n_pts=pts.shape[0], points_3d=pts + rng.normal(0, 2.0, pts.shape),
+                             points_2d=uv[pi, ci] + rng.normal(0, 0.3, (pi.size, 2)),
+                             camera_ind=ci, point_ind=pi))
+    n_cams, points_3d, points_2d, camera_ind, point_ind = lio.concat_points_dataset(datasets)
+    cams0 = cams_gt.copy()
+    cams0[:, :3] += rng.normal(0, 1e-3, (C, 3))
+    cams0[:, 3:6] += rng.normal(0, 1.0, (C, 3))
+    sba = PySBA(cams0, points_3d, points_2d, camera_ind, point_ind)
+    r0 = sba.project(sba.points3D[sba.point2DIndices], sba.cameraArray[sba.cameraIndices]) - sba.points2D
+    res = sba.bundleAdjust(1e-4, verbose=0)
+    r1 = sba.project(sba.points3D[sba.point2DIndices], sba.cameraArray[sba.cameraIndices]) - sba.points2D
+    assert res.success and np.sqrt((r1 ** 2).sum(1)).mean() < 0.1 * np.sqrt((r0 ** 2).sum(1)).mean()
+    ora = O.trf_exact(cams0, points_3d, points_2d, camera_ind, point_ind, ftol=1e-4)
+    assert res.nfev == ora.nfev
+    np.testing.assert_allclose(res.cost, ora.cost, rtol=1e-7)
+    cam_list = [lio.sba_to_readable_format(sba.cameraArray[i, :]) for i in range(n_cams)]
+    red = lio.readable_to_red_format(cam_list)
+    assert red.shape == (C, 25) and np.all(np.isfinite(red))
+    assert pickle.loads(pickle.dumps(sba)).cameraArray.shape == (C, 11)
+
+
 # ----------------------------------------------------------------------------- error paths
 def test_error_behaviour(PySBA, Engine):
     from lasercalib_b200._cabi import LcbaError
