@@ -151,6 +151,23 @@ int lcba_unproject(lcba_t* h, int64_t M, const double* uv, const double* Z, int6
                    const double* camera_matrix, const double* dist5, const double* rc_ext,
                    const double* tc_ext, double* out_xyz);
 
+/* ---- squared-residual variants: fun_camonly (pySBA.py:151-156, driver :160-173) and
+ * fun_transform_points_3d (pySBA.py:176-188, driver :191-206) --------------------------
+ * f = w (proj - obs)^2 per pixel coordinate; the reference hands these to a DENSE scipy
+ * least_squares.  One pass over the resident observations returns cost = 0.5 sum f^2,
+ * g = J^T f and J^T J (analytic J = 2 w e dproj/dtheta); the n x n trust-region arithmetic
+ * stays with the caller (lasercalib_b200/_trf_dense.py).
+ *   LCBA_SQ_CAMONLY  : theta = (C,11) cameras, the handle's points fixed;
+ *                      g (11C), H (C,11,11) = the diagonal blocks (cameras do not couple)
+ *   LCBA_SQ_TRANSFORM: theta = 12 = rows of [A|t] applied to the handle's points, the
+ *                      handle's cameras fixed; g (12), H (12,12)
+ * g and H both NULL = cost only.  Sums run over this handle's observations only (no
+ * collective: under torchrun the variants run as replicas). */
+#define LCBA_SQ_CAMONLY 0
+#define LCBA_SQ_TRANSFORM 1
+int lcba_sq_normal(lcba_t* h, int32_t mode, const double* theta, double* cost_out, double* g_out,
+                   double* H_out);
+
 /* ---- PySBA.fun (pySBA.py:92-101) --------------------------------------------------
  * x_or_null: 11C + 3P parameters (NULL = the handle's current x). r_out: 2N or NULL. */
 int lcba_residuals(lcba_t* h, const double* x_or_null, double* r_out, double* cost_out);

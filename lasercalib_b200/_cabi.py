@@ -19,7 +19,8 @@ SYMBOLS = ["lcba_version", "lcba_create", "lcba_destroy", "lcba_last_error", "lc
            "lcba_set_problem", "lcba_set_problem_shard", "lcba_set_params", "lcba_get_params", "lcba_rotate", "lcba_project",
            "lcba_unproject", "lcba_residuals", "lcba_jacobian_blocks", "lcba_sparsity_indices", "lcba_solve",
            "lcba_get_trace", "lcba_get_grad", "lcba_get_profile", "lcba_linearize",
-           "lcba_time_device", "lcba_nccl_unique_id", "lcba_comm_init", "lcba_debug_tr2d"]
+           "lcba_time_device", "lcba_nccl_unique_id", "lcba_comm_init", "lcba_debug_tr2d",
+           "lcba_sq_normal"]
 
 
 class Options(C.Structure):
@@ -92,6 +93,7 @@ def load():
     lib.lcba_time_device.argtypes = [vp, i32, i32, pd]
     lib.lcba_nccl_unique_id.argtypes = [vp]
     lib.lcba_comm_init.argtypes = [vp, i32, i32, vp]
+    lib.lcba_sq_normal.argtypes = [vp, i32, vp, pd, vp, vp]
     lib.lcba_debug_tr2d.argtypes = [dbl, dbl, dbl, dbl, dbl, dbl, pd, C.POINTER(C.c_int)]
     _lib = lib
     return lib
@@ -206,6 +208,23 @@ class Engine:
         cost = C.c_double()
         self._check(self.lib.lcba_residuals(self.h, _ptr(x), _ptr(r), C.byref(cost)))
         return r, cost.value
+
+    SQ_CAMONLY, SQ_TRANSFORM = 0, 1
+
+    def sq_normal(self, mode, theta, derivs=True):
+        """(cost, g, H) of the squared-residual variants at theta (lcba_sq_normal): camera-only
+        mode returns H as the (C,11,11) diagonal blocks, transform mode as (12,12)."""
+        theta = _f64(theta).ravel()
+        n = 11 * self.C if mode == self.SQ_CAMONLY else 12
+        if theta.size != n:
+            raise ValueError("theta has the wrong size")
+        cost = C.c_double()
+        g = H = None
+        if derivs:
+            g = np.empty(n)
+            H = np.empty((self.C, 11, 11)) if mode == self.SQ_CAMONLY else np.empty((12, 12))
+        self._check(self.lib.lcba_sq_normal(self.h, int(mode), _ptr(theta), C.byref(cost), _ptr(g), _ptr(H)))
+        return cost.value, g, H
 
     def jacobian_blocks(self, x=None):
         x = None if x is None else _f64(x).ravel()

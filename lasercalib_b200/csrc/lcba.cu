@@ -17,6 +17,7 @@
 #include "ingest.cuh"
 #include "linearize.cuh"
 #include "schur.cuh"
+#include "variants.cuh"
 
 using namespace lcba;
 
@@ -106,6 +107,8 @@ struct lcba_handle {
   int rank = 0, nranks = 1;
   int fix_cameras = 0, shared_intr = 0;
   double *d_pred = nullptr, *d_scl_red = nullptr;   // shared-intrinsics mode: reduced step / scale
+  double *d_sqpart = nullptr, *d_sqout = nullptr, *d_theta = nullptr;   // squared-residual variants
+  int sq_grid = 0, sq_K = 0;
 };
 
 static std::string g_last_error;
@@ -231,6 +234,7 @@ extern "C" int lcba_create(lcba_t** out, int device) {
                                       (const void*)k_schur<true, 160>, (const void*)k_schur<false, 160>,
                                       (const void*)k_schur<true, 128>, (const void*)k_schur<false, 128>,
                                       (const void*)k_residual,
+                                      (const void*)k_sq_camonly<true>, (const void*)k_sq_camonly<false>,
                                       (const void*)k_jdot,      (const void*)k_jacobian_blocks};
     for (const void* f : big_smem_kernels) {
       cudaFuncAttributes fa;
@@ -292,6 +296,7 @@ extern "C" int lcba_set_problem_shard(lcba_t* h, int32_t C, int64_t P, int64_t N
   dev_free_all(h);
   h->have_problem = false;
   h->d_rout = nullptr; h->d_Jc = nullptr; h->d_Jp = nullptr;
+  h->d_sqpart = nullptr; h->d_sqout = nullptr; h->d_theta = nullptr; h->sq_grid = 0; h->sq_K = 0;
   h->C = C; h->P = P; h->N = N; h->P_total = P; h->cur = 0;
   cudaStream_t st = h->stream;
 
@@ -1152,6 +1157,84 @@ extern "C" int lcba_debug_schur_stats(lcba_t* h, long long* out, int max_ctas, i
   cudaMemcpy(out, h->d_stats, (size_t)n * 4 * sizeof(long long), cudaMemcpyDeviceToHost);
   *nkinds = h->plan.nkinds;
   *nslices = h->plan.nslices;
+  return LCBA_OK;
+}
+
+// ---- squared-residual variants (pySBA.py:151-206): cost, J^T f, J^T J in one pass ----------
+extern "C" int lcba_sq_normal(lcba_t* h, int32_t mode, const double* theta, double* cost_out,
+                              double* g_out, double* H_out) {
+  if (!h || !h->have_problem) { set_error(h, "lcba_sq_normal: no problem set"); return LCBA_E_STATE; }
+  if (!theta || (mode != LCBA_SQ_CAMONLY && mode != LCBA_SQ_TRANSFORM) || ((g_out == nullptr) != (H_out == nullptr))) {
+    set_error(h, "lcba_sq_normal: bad mode, NULL theta, or only one of g / H given");
+    return LCBA_E_ARG;
+  }
+  cudaSetDevice(h->device);
+  const int C = h->C;
+  const bool derivs = g_out != nullptr;
+  const int K = (mode == LCBA_SQ_CAMONLY ? C * SQC_VALS : SQT_VALS) + 1;
+  const int warps = sq_camonly_warps(C, h->smem_optin);
+  const int threads = (mode == LCBA_SQ_CAMONLY) ? warps * 32 : SQ_THREADS;
+  const int per_sm = (mode == LCBA_SQ_CAMONLY) ? 1 : 2;
+  const int grid = (int)std::max<long long>(1, std::min<long long>((h->N + threads - 1) / threads,
+                                                                   (long long)h->sm_count * per_sm));
+  if (!h->d_sqpart || h->sq_grid < grid || h->sq_K < K) {
+    LCBA_TRY(dev_alloc(h, &h->d_sqpart, (size_t)grid * K));
+    LCBA_TRY(dev_alloc(h, &h->d_sqout, (size_t)K));
+    if (!h->d_theta) LCBA_TRY(dev_alloc(h, &h->d_theta, 16));
+    h->sq_grid = grid;
+    h->sq_K = K;
+  }
+  const int cur = h->cur, scratch = 1 - h->cur;
+  if (mode == LCBA_SQ_CAMONLY) {
+    LCBA_CUDA(h, cudaMemcpyAsync(h->d_cams[scratch], theta, (size_t)C * NCP * 8, cudaMemcpyHostToDevice, h->stream));
+    LCBA_TRY(build_tables(h, scratch));
+    const size_t smem = ((size_t)((C * CAMTAB + 1) & ~1) + (derivs ? (size_t)warps * C * SQC_VALS : 0)) * 8;
+    if (derivs)
+      KL(h, "sq_camonly", k_sq_camonly<true><<<grid, threads, smem, h->stream>>>(
+            h->d_tab[scratch], h->d_pts[cur], h->d_uv, h->d_cam, h->d_pt, h->d_w, h->N, C, h->d_sqpart));
+    else
+      KL(h, "sq_camonly_cost", k_sq_camonly<false><<<grid, threads, smem, h->stream>>>(
+            h->d_tab[scratch], h->d_pts[cur], h->d_uv, h->d_cam, h->d_pt, h->d_w, h->N, C, h->d_sqpart));
+  } else {
+    LCBA_CUDA(h, cudaMemcpyAsync(h->d_theta, theta, 12 * 8, cudaMemcpyHostToDevice, h->stream));
+    LCBA_TRY(build_tables(h, cur));
+    const size_t smem = (size_t)((C * CAMTAB + 1) & ~1) * 8;
+    if (derivs)
+      KL(h, "sq_transform", k_sq_transform<true><<<grid, threads, smem, h->stream>>>(
+            h->d_tab[cur], h->d_pts[cur], h->d_uv, h->d_cam, h->d_pt, h->d_w, h->N, C, h->d_theta, h->d_sqpart));
+    else
+      KL(h, "sq_transform_cost", k_sq_transform<false><<<grid, threads, smem, h->stream>>>(
+            h->d_tab[cur], h->d_pts[cur], h->d_uv, h->d_cam, h->d_pt, h->d_w, h->N, C, h->d_theta, h->d_sqpart));
+  }
+  KL(h, "reduce", k_reduce_cols<<<nblk(K, 128), 128, 0, h->stream>>>(h->d_sqpart, grid, K, h->d_sqout));
+  std::vector<double> v((size_t)K);
+  LCBA_CUDA(h, cudaMemcpyAsync(v.data(), h->d_sqout, (size_t)K * 8, cudaMemcpyDeviceToHost, h->stream));
+  LCBA_CUDA(h, cudaStreamSynchronize(h->stream));
+  LCBA_TRY(check_launch(h, "lcba_sq_normal"));
+  if (cost_out) *cost_out = 0.5 * v[K - 1];
+  if (!derivs) return LCBA_OK;
+  if (mode == LCBA_SQ_CAMONLY) {
+    for (int c = 0; c < C; ++c) {
+      const double* s = v.data() + (size_t)c * SQC_VALS;
+      double* Hc = H_out + (size_t)c * NCP * NCP;
+      int idx = 0;
+      for (int a = 0; a < NCP; ++a)
+        for (int b = a; b < NCP; ++b, ++idx) Hc[a * NCP + b] = Hc[b * NCP + a] = s[idx];
+      for (int a = 0; a < NCP; ++a) g_out[(size_t)c * NCP + a] = s[66 + a];
+    }
+  } else {
+    // J^T J [(k,j),(l,i)] = sum M[k,l] Q[j,i]
+    int mi[3][3], qi[4][4], n = 0;
+    for (int k = 0; k < 3; ++k) for (int l = k; l < 3; ++l) mi[k][l] = mi[l][k] = n++;
+    n = 0;
+    for (int j = 0; j < 4; ++j) for (int i = j; i < 4; ++i) qi[j][i] = qi[i][j] = n++;
+    for (int k = 0; k < 3; ++k)
+      for (int j = 0; j < 4; ++j)
+        for (int l = 0; l < 3; ++l)
+          for (int i = 0; i < 4; ++i)
+            H_out[(4 * k + j) * 12 + 4 * l + i] = v[(size_t)mi[k][l] * SQT_Q + qi[j][i]];
+    for (int a = 0; a < 12; ++a) g_out[a] = v[60 + a];
+  }
   return LCBA_OK;
 }
 

@@ -336,13 +336,55 @@ class PySBA:
         return out
 
     # ---- variants of the reference that are not on the production path ----
-    def _next_row(self, name):
-        raise NotImplementedError(
-            "%s is a 'next' row of the hot-path scope table (SURVEY.md section 8f): not built "
-            "yet; there is deliberately no CPU fallback" % name)
+    # ---- the two dense squared-residual variants (pySBA.py:151-206) ----
+    def _dense_variant(self, mode, x0, ftol, verbose):
+        """scipy's dense trf loop (tr_solver='exact', x_scale=1) with cost / J^T f / J^T J
+        evaluated on the GPU in one pass per call; only n x n arithmetic runs here."""
+        from ._trf_dense import trf_dense
+        cams = np.ascontiguousarray(self.cameraArray, dtype=np.float64)
+        pts = np.ascontiguousarray(self.points3D, dtype=np.float64)
+        eng = self._ensure_problem(cams, pts, self.cameraIndices, self.point2DIndices,
+                                   self.points2D, self.pointWeights)
+        eng.set_params(cams, pts)
+        C = cams.shape[0]
+        launches0 = [0]
 
-    def bundle_adjustment_camonly(self, ftol=1e-4):
-        self._next_row("bundle_adjustment_camonly")
+        def evaluate(x, derivs):
+            cost, g, H = eng.sq_normal(mode, x, derivs)
+            launches0[0] += 3
+            if derivs and mode == eng.SQ_CAMONLY:
+                D = np.zeros((C * N_CAM_PARAMS, C * N_CAM_PARAMS))
+                for c in range(C):
+                    a = c * N_CAM_PARAMS
+                    D[a:a + N_CAM_PARAMS, a:a + N_CAM_PARAMS] = H[c]
+                H = D
+            return cost, g, H
+
+        m = 2 * np.asarray(self.cameraIndices).size
+        r = trf_dense(evaluate, x0, m, ftol, verbose=verbose,
+                      block=N_CAM_PARAMS if mode == eng.SQ_CAMONLY else None)
+        out = BAResult(x=r.x, cost=r.cost, grad=r.grad, optimality=r.optimality,
+                       active_mask=r.active_mask, nfev=r.nfev, njev=r.njev, status=r.status,
+                       message=r.message, success=r.success)
+        out["gpu_launches"] = launches0[0]
+        return out
+
+    def _squared_fun(self, cams, pts):
+        w = np.asarray(self.pointWeights, dtype=np.float64).reshape(-1, 1)
+        e = self.project(pts[self.point2DIndices], cams[self.cameraIndices]) - self.points2D
+        return (w * e ** 2).ravel()
+
+    def bundle_adjustment_camonly(self, ftol=1e-4, verbose=2):
+        """Optimise the cameras with the 3-D points fixed (pySBA.py:158-173).  As in the
+        reference the residual is w * (proj - obs)**2 and the solve is scipy's dense
+        `least_squares(method='trf')` with default options; `res.x` = cameras (11 C)."""
+        C = self.cameraArray.shape[0]
+        x0 = np.asarray(self.cameraArray, dtype=np.float64).ravel()
+        out = self._dense_variant(_cabi.Engine.SQ_CAMONLY, x0, ftol, verbose)
+        self.cameraArray = out.x.reshape((C, N_CAM_PARAMS))
+        cams, pts = self.cameraArray, np.asarray(self.points3D, dtype=np.float64)
+        out.set_lazy("fun", lambda: self._squared_fun(cams, pts))
+        return out
 
     def _finish_nocam(self, eng, res, pts, shard, verbose):
         x = pts.ravel().copy()
@@ -379,8 +421,18 @@ class PySBA:
         camera | points]; ``cameraArray`` gets the shared intrinsics tiled."""
         return self.bundleAdjust(ftol, _shared=True)
 
-    def bundleAdjust_transform_points_3d(self, ftol=1e-3):
-        self._next_row("bundleAdjust_transform_points_3d")
+    def bundleAdjust_transform_points_3d(self, ftol=1e-3, verbose=2):
+        """Fit one 12-parameter affine map [A|t] of all 3-D points with the cameras fixed
+        (pySBA.py:176-206; squared residuals, dense solve, x0 = identity); `points3D` is
+        replaced by the transformed points, `res.x` = rows of [A|t]."""
+        x0 = np.hstack((np.eye(3), np.zeros((3, 1)))).ravel()
+        out = self._dense_variant(_cabi.Engine.SQ_TRANSFORM, x0, ftol, verbose)
+        M = out.x.reshape((3, 4))
+        pts = np.asarray(self.points3D, dtype=np.float64)
+        self.points3D = pts @ M[:, :3].T + M[:, 3]
+        cams, new_pts = np.asarray(self.cameraArray, dtype=np.float64), self.points3D
+        out.set_lazy("fun", lambda: self._squared_fun(cams, new_pts))
+        return out
 
     def getResiduals(self):
         """Residuals at the current parameters with unit weights (pySBA.py:207-213; the

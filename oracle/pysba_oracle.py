@@ -721,6 +721,86 @@ def trf_exact_sharedcam(cams, pts, points_2d, camera_indices, point_indices, wei
                              ftol, **kw)
 
 
+# ------------------------------------------- squared-residual dense variants
+def fun_camonly(params, n_cameras, camera_indices, point_indices, points_2d, weights, points_3d):
+    """pySBA.py:151-156: cameras only, points fixed, residual = w * (proj - obs)**2."""
+    cams = params.reshape(n_cameras, NCP)
+    uv = project(points_3d[point_indices], cams[camera_indices])
+    return (weights * (uv - points_2d) ** 2).ravel()
+
+
+def bundle_adjust_camonly(cams, pts, points_2d, camera_indices, point_indices, weights=None,
+                          ftol=1e-4, verbose=0, **ls_kwargs):
+    """pySBA.py:160-173: dense least_squares, every option but ftol at scipy's default
+    (2-point Jacobian, tr_solver 'exact', x_scale 1).  Returns (res, cams_out)."""
+    C = cams.shape[0]
+    if weights is None:
+        weights = default_weights(point_indices)
+    weights = np.asarray(weights).reshape(-1, 1)
+    res = least_squares(fun_camonly, cams.ravel(), verbose=verbose, ftol=ftol, method="trf",
+                        args=(C, camera_indices, point_indices, points_2d, weights, pts),
+                        **ls_kwargs)
+    return res, res.x.reshape(C, NCP)
+
+
+def apply_transform(theta, pts):
+    """Rows of [A | t] (3x4, row-major 12-vector) applied to points (pySBA.py:177-184)."""
+    M = np.asarray(theta).reshape(3, 4)
+    return pts @ M[:, :3].T + M[:, 3]
+
+
+def fun_transform_points_3d(theta, cams, camera_indices, point_indices, points_2d, weights,
+                            points_3d):
+    """pySBA.py:176-188: one 12-parameter affine map of all points, cameras fixed,
+    residual = w * (proj - obs)**2."""
+    X = apply_transform(theta, points_3d)
+    uv = project(X[point_indices], cams[camera_indices])
+    return (weights * (uv - points_2d) ** 2).ravel()
+
+
+def bundle_adjust_transform_points_3d(cams, pts, points_2d, camera_indices, point_indices,
+                                      weights=None, ftol=1e-3, verbose=0, **ls_kwargs):
+    """pySBA.py:191-206.  Returns (res, transformed points)."""
+    if weights is None:
+        weights = default_weights(point_indices)
+    weights = np.asarray(weights).reshape(-1, 1)
+    x0 = np.hstack((np.eye(3), np.zeros((3, 1)))).ravel()
+    res = least_squares(fun_transform_points_3d, x0, verbose=verbose, ftol=ftol, method="trf",
+                        args=(cams, camera_indices, point_indices, points_2d, weights, pts),
+                        **ls_kwargs)
+    return res, apply_transform(res.x, pts)
+
+
+def sq_normal_camonly(cams, pts, points_2d, camera_indices, point_indices, weights=None):
+    """Analytic (cost, g (11C), H (C,11,11)) of fun_camonly: f = w e^2, J = 2 w e dproj."""
+    C = cams.shape[0]
+    w = np.ones(camera_indices.size) if weights is None else np.asarray(weights, float).reshape(-1)
+    uv, Jc, _ = jacobian_blocks(cams, pts, camera_indices, point_indices)
+    e = uv - points_2d
+    f = w[:, None] * e * e
+    J = 2.0 * (w[:, None] * e)[:, :, None] * Jc
+    H = np.zeros((C, NCP, NCP))
+    g = np.zeros((C, NCP))
+    np.add.at(H, camera_indices, np.einsum("nia,nib->nab", J, J))
+    np.add.at(g, camera_indices, np.einsum("nia,ni->na", J, f))
+    return 0.5 * np.sum(f * f), g.ravel(), H
+
+
+def sq_normal_transform(theta, cams, pts, points_2d, camera_indices, point_indices, weights=None):
+    """Analytic (cost, g (12), H (12,12)) of fun_transform_points_3d."""
+    w = np.ones(camera_indices.size) if weights is None else np.asarray(weights, float).reshape(-1)
+    X = apply_transform(theta, pts)
+    uv, _, Jp = jacobian_blocks(cams, X, camera_indices, point_indices)
+    e = uv - points_2d
+    f = w[:, None] * e * e
+    Xh = np.column_stack([pts, np.ones(pts.shape[0])])[point_indices]      # (N,4)
+    # d proj_d / d theta[k,j] = Jp[d,k] * Xh[j]
+    Jt = np.einsum("ndk,nj->ndkj", Jp, Xh).reshape(-1, 2, 12)
+    J = 2.0 * (w[:, None] * e)[:, :, None] * Jt
+    Jf = J.reshape(-1, 12)
+    return 0.5 * np.sum(f * f), Jf.T @ f.ravel(), Jf.T @ Jf
+
+
 def rmse_px(res_vec):
     """sqrt(mean(|r_i|^2)) over observations, r_i the 2-vector pixel residual."""
     r = np.asarray(res_vec).reshape(-1, 2)

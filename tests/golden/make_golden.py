@@ -205,6 +205,44 @@ def golden_sharedcam():
     print("ba_sharedcam_ring8_500: cost", res.cost, "nfev", res.nfev, "status", res.status)
 
 
+def golden_squared():
+    """The two dense squared-residual variants (pySBA.py:151-206) through the reference:
+    bundle_adjustment_camonly on an 8-camera rig (points at ground truth, cameras perturbed)
+    and bundleAdjust_transform_points_3d (cameras at ground truth, points moved by a known
+    affine map).  Also records fun at x0 so the restated residual functions are pinned."""
+    pb = make_rig("ring8", 400, seed=21, variant="volume", p_vis=0.85)
+    sba = PySBA(pb["cams0"].copy(), pb["pts_gt"].copy(), pb["points_2d"], pb["camera_ind"],
+                pb["point_ind"])
+    f0 = sba.fun_camonly(pb["cams0"].ravel(), 8, pb["n_points"], pb["camera_ind"], pb["point_ind"],
+                         pb["points_2d"], sba.pointWeights, pb["pts_gt"])
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        res = sba.bundle_adjustment_camonly(1e-4)
+    np.savez_compressed(os.path.join(HERE, "ba_camonly_ring8_400.npz"), ref_x=res.x, ref_f0=f0,
+                        ref_cost=res.cost, ref_nfev=res.nfev, ref_njev=res.njev,
+                        ref_status=res.status, ref_cams=sba.cameraArray, ref_log=buf.getvalue(),
+                        **inputs_of(pb), **VERS)
+    print("ba_camonly_ring8_400: cost", res.cost, "nfev", res.nfev, "status", res.status)
+
+    rng = np.random.default_rng(5)
+    A = np.eye(3) + 0.02 * rng.normal(size=(3, 3))
+    t = np.array([4.0, -3.0, 6.0])
+    moved = (pb["pts_gt"] - t) @ np.linalg.inv(A).T          # A moved + t = pts_gt
+    sba = PySBA(pb["cams_gt"].copy(), moved.copy(), pb["points_2d"], pb["camera_ind"],
+                pb["point_ind"])
+    x0 = np.hstack((np.eye(3), np.zeros((3, 1)))).ravel()
+    f0 = sba.fun_transform_points_3d(x0, 8, pb["n_points"], pb["cams_gt"], pb["camera_ind"], pb["point_ind"],
+                                     pb["points_2d"], sba.pointWeights, moved)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        res = sba.bundleAdjust_transform_points_3d(1e-3)
+    np.savez_compressed(os.path.join(HERE, "ba_transform_ring8_400.npz"), ref_x=res.x, ref_f0=f0,
+                        ref_cost=res.cost, ref_nfev=res.nfev, ref_njev=res.njev,
+                        ref_status=res.status, ref_points=sba.points3D, moved=moved, A=A, t=t,
+                        ref_log=buf.getvalue(), **inputs_of(pb), **VERS)
+    print("ba_transform_ring8_400: cost", res.cost, "nfev", res.nfev, "status", res.status)
+
+
 def golden_io():
     """Export / init formats of lasercalib/convert_params.py on the 17 example cameras."""
     import cv2
@@ -251,7 +289,7 @@ def golden_unproject():
 
 if __name__ == "__main__":
     only = {"--only-unproject": golden_unproject, "--only-sharedcam": golden_sharedcam,
-            "--only-io": golden_io, "--only-nocam": golden_nocam}
+            "--only-io": golden_io, "--only-nocam": golden_nocam, "--only-squared": golden_squared}
     picked = [fn for flag, fn in only.items() if flag in sys.argv]
     if picked:
         for fn in picked:
@@ -259,6 +297,7 @@ if __name__ == "__main__":
         sys.exit(0)
     golden_nocam()
     golden_sharedcam()
+    golden_squared()
     golden_model()
     golden_example_cams()
     golden_ba("ba_ring4_planar2000", "ring4", 2000, "planar")

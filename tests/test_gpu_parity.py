@@ -449,6 +449,88 @@ def test_calibrate_camera_script_flow(PySBA, golden):
     assert pickle.loads(pickle.dumps(sba)).cameraArray.shape == (C, 11)
 
 
+# ------------------------------------------------ dense squared-residual variants (8f rank 1)
+def test_sq_normal_matches_oracle(Engine, golden):
+    """lcba_sq_normal (cost, J^T f, J^T J in one pass) against the analytic numpy restatement;
+    weighted and unweighted, shuffled input, 18 cameras with partial visibility."""
+    for pb, weights in ((make_rig("ring8", 500, seed=2, p_vis=0.8), None),
+                        (shuffle_observations(make_rig("example18", 400, seed=3, p_vis=0.6), seed=1), "w")):
+        ci, pi, uv = pb["camera_ind"], pb["point_ind"], pb["points_2d"]
+        w = None if weights is None else np.random.default_rng(0).uniform(0.5, 2.0, ci.size)
+        eng = Engine()
+        eng.set_problem(pb["cams_gt"], pb["pts0"], uv, ci, pi, w)
+        cost, g, H = eng.sq_normal(eng.SQ_CAMONLY, pb["cams0"])
+        oc, og, oH = O.sq_normal_camonly(pb["cams0"], pb["pts0"], uv, ci, pi, w)
+        np.testing.assert_allclose(cost, oc, rtol=1e-12)
+        np.testing.assert_allclose(g, og, rtol=1e-9, atol=1e-9 * np.abs(og).max())
+        np.testing.assert_allclose(H, oH, rtol=1e-9, atol=1e-9 * np.abs(oH).max())
+        c2, g2, H2 = eng.sq_normal(eng.SQ_CAMONLY, pb["cams0"], derivs=False)
+        assert g2 is None and H2 is None
+        np.testing.assert_allclose(c2, oc, rtol=1e-12)
+        th = np.hstack((np.eye(3) + 0.01, np.array([[1.0], [-2.0], [0.5]]))).ravel()
+        cost, g, H = eng.sq_normal(eng.SQ_TRANSFORM, th)
+        oc, og, oH = O.sq_normal_transform(th, pb["cams_gt"], pb["pts0"], uv, ci, pi, w)
+        np.testing.assert_allclose(cost, oc, rtol=1e-12)
+        np.testing.assert_allclose(g, og, rtol=1e-9, atol=1e-9 * np.abs(og).max())
+        np.testing.assert_allclose(H, oH, rtol=1e-9, atol=1e-9 * np.abs(oH).max())
+        np.testing.assert_allclose(eng.sq_normal(eng.SQ_TRANSFORM, th, derivs=False)[0], oc, rtol=1e-12)
+        eng.close()
+
+
+def test_camonly_matches_reference_run(PySBA, golden):
+    """PySBA.bundle_adjustment_camonly against the reference's own run (golden) and against
+    scipy fed the analytic Jacobian (the oracle arm that has no finite-difference noise)."""
+    from scipy.optimize import least_squares
+    g = golden("ba_camonly_ring8_400")
+    ci, pi, uv, pts = g["camera_ind"], g["point_ind"], g["points_2d"], g["pts_gt"]
+    C, N = g["cams0"].shape[0], ci.size
+    sba = PySBA(g["cams0"].copy(), pts.copy(), uv, ci, pi)
+    buf = io.StringIO()
+    with redirect_stdout(buf):
+        res = sba.bundle_adjustment_camonly(1e-4)
+    assert (res.nfev, res.njev, res.status) == (int(g["ref_nfev"]), int(g["ref_njev"]), int(g["ref_status"]))
+    np.testing.assert_allclose(res.cost, g["ref_cost"], rtol=1e-5)      # reference: 2-point FD
+    assert buf.getvalue().splitlines()[0].split() == g["ref_log"].item().splitlines()[0].split()
+    assert len(buf.getvalue().splitlines()) == len(g["ref_log"].item().splitlines())
+    uv_a = O.project(pts[pi], sba.cameraArray[ci])
+    uv_b = O.project(pts[pi], g["ref_cams"][ci])
+    assert np.abs(uv_a - uv_b).max() < 1e-2
+    np.testing.assert_allclose(res.fun, O.fun_camonly(res.x, C, ci, pi, uv, np.ones((N, 1)), pts),
+                               rtol=1e-9, atol=1e-12)
+
+    def jac(x, *a):
+        p, Jc, _ = O.jacobian_blocks(x.reshape(C, 11), pts, ci, pi)
+        Jd = 2 * (p - uv)[:, :, None] * Jc
+        D = np.zeros((2 * N, 11 * C))
+        for d in range(2):
+            for a_ in range(11):
+                D[2 * np.arange(N) + d, ci * 11 + a_] = Jd[:, d, a_]
+        return D
+
+    ref = least_squares(O.fun_camonly, g["cams0"].ravel(), jac=jac, ftol=1e-4, method="trf",
+                        args=(C, ci, pi, uv, np.ones((N, 1)), pts))
+    assert (res.nfev, res.njev, res.status) == (ref.nfev, ref.njev, ref.status)
+    np.testing.assert_allclose(res.cost, ref.cost, rtol=1e-9)
+    np.testing.assert_allclose(res.x, ref.x, rtol=1e-5, atol=1e-8)
+
+
+def test_transform_points_3d_matches_reference_run(PySBA, golden):
+    g = golden("ba_transform_ring8_400")
+    ci, pi, uv = g["camera_ind"], g["point_ind"], g["points_2d"]
+    sba = PySBA(g["cams_gt"].copy(), g["moved"].copy(), uv, ci, pi)
+    res = sba.bundleAdjust_transform_points_3d(1e-3, verbose=0)
+    assert (res.nfev, res.njev, res.status) == (int(g["ref_nfev"]), int(g["ref_njev"]), int(g["ref_status"]))
+    np.testing.assert_allclose(res.cost, g["ref_cost"], rtol=1e-5)
+    np.testing.assert_allclose(sba.points3D, g["ref_points"], rtol=1e-5, atol=1e-4)
+    # the known map is recovered up to the pixel noise
+    M = res.x.reshape(3, 4)
+    np.testing.assert_allclose(M[:, :3], g["A"], atol=2e-3)
+    np.testing.assert_allclose(M[:, 3], g["t"], atol=0.5)
+    # a second call starts from the transformed points: the identity is (nearly) optimal
+    res2 = sba.bundleAdjust_transform_points_3d(1e-3, verbose=0)
+    np.testing.assert_allclose(res2.x.reshape(3, 4)[:, :3], np.eye(3), atol=1e-3)
+
+
 # ----------------------------------------------------------------------------- error paths
 def test_error_behaviour(PySBA, Engine):
     from lasercalib_b200._cabi import LcbaError
@@ -471,8 +553,9 @@ def test_error_behaviour(PySBA, Engine):
         Engine().solve()
     with pytest.raises(LcbaError, match="64 cameras"):
         eng.set_problem(np.zeros((65, 11)), pb["pts0"], pb["points_2d"], pb["camera_ind"], pb["point_ind"])
-    with pytest.raises(NotImplementedError):
-        sba.bundle_adjustment_camonly()
+    with pytest.raises(ValueError, match="wrong size"):
+        eng.set_problem(pb["cams0"], pb["pts0"], pb["points_2d"], pb["camera_ind"], pb["point_ind"])
+        eng.sq_normal(eng.SQ_TRANSFORM, np.zeros(11))
     eng.close()
 
 
