@@ -413,11 +413,11 @@ extern "C" int lcba_set_problem_shard(lcba_t* h, int32_t C, int64_t P, int64_t N
   LCBA_TRY(dev_alloc(h, &h->d_pred, (size_t)n));
   LCBA_TRY(dev_alloc(h, &h->d_scl_red, (size_t)n));
   LCBA_TRY(dev_alloc(h, &h->d_S, (size_t)n * n));
-  LCBA_TRY(dev_alloc(h, &h->d_Lf, (size_t)n * n));
+  LCBA_TRY(dev_alloc(h, &h->d_Lf, (size_t)(n + 1) * n));   // + rhs row (k_chol_fused)
   LCBA_TRY(dev_alloc(h, &h->d_rhs, (size_t)n));
   LCBA_TRY(dev_alloc(h, &h->d_red, 64));
   LCBA_TRY(dev_alloc(h, &h->d_coef, 2));
-  LCBA_TRY(dev_alloc(h, &h->d_fail, 1));
+  LCBA_TRY(dev_alloc(h, &h->d_fail, 2));   // [0] failure bits, [1] grid-barrier counter
   LCBA_TRY(dev_alloc(h, &h->d_ctl, 1));
   // grids: persistent-style, a multiple of the SM count
   const size_t lin_smem = linearize_smem_doubles(C) * 8;
@@ -780,23 +780,45 @@ __global__ void k_assemble_S_ctl(const double* __restrict__ red, int C, int npai
 // Cholesky of S + mu*Dc^2, solve for the camera step
 static int pass_camera_solve(lcba_t* h, double mu) {
   const int n = h->shared_intr ? 3 + 8 * h->C : h->C * NCP;
-  LCBA_CUDA(h, cudaMemsetAsync(h->d_fail, 0, sizeof(int), h->stream));
-  KL(h, "chol_copy", k_copy_damped<<<nblk((long long)n * n, 256), 256, 0, h->stream>>>(
-        h->d_S, n, mu, h->shared_intr ? h->d_scl_red : h->d_scl_c, h->d_Lf));
-  for (int k = 0; k < n; k += CH_NB) {
-    KL(h, "chol_panel", k_chol_panel<<<1, 256, 0, h->stream>>>(h->d_Lf, n, k, h->d_fail));
-    const int rem = n - k - CH_NB;
-    if (rem > 0) {
-      const int nt = (rem + CH_NB - 1) / CH_NB;
-      KL(h, "chol_update", k_chol_update<<<dim3(nt, nt), 256, 0, h->stream>>>(h->d_Lf, n, k));
+  LCBA_CUDA(h, cudaMemsetAsync(h->d_fail, 0, 2 * sizeof(int), h->stream));
+  const double* scl = h->shared_intr ? h->d_scl_red : h->d_scl_c;
+  double* out = h->shared_intr ? h->d_pred : h->d_pc;
+  {
+    KL(h, "chol_copy", k_copy_damped_rhs<<<nblk((long long)(n + 1) * n, 256), 256, 0, h->stream>>>(
+          h->d_S, n, mu, scl, h->d_rhs, h->d_Lf));
+    // grid = trailing tiles of the first panel (one tile per CTA), capped; all CTAs co-resident
+    int tiles = 1;
+    if (n > CH_NB) {
+      const int ntr = (n + 1 - CH_NB + CH_NB - 1) / CH_NB, ntc = (n - CH_NB + CH_NB - 1) / CH_NB;
+      tiles = 0;
+      for (int ti = 0; ti < ntr; ++ti) tiles += std::min(ti + 1, ntc);
+    }
+    static const int cap = getenv("LCBA_CHOL_GRID") ? atoi(getenv("LCBA_CHOL_GRID")) : 64;
+    int grid = std::max(1, std::min(tiles, std::min(cap, h->sm_count)));
+    double* A = h->d_Lf;
+    int nn = n;
+    int* sync = h->d_fail;
+    static long long* dbg = nullptr;
+    static const bool want_dbg = getenv("LCBA_CHOL_DBG") != nullptr;
+    if (want_dbg && !dbg) cudaMalloc(&dbg, 6 * sizeof(long long));
+    void* args[] = {(void*)&A, (void*)&nn, (void*)&out, (void*)&sync, (void*)&dbg};
+    KL(h, "chol_fused", {
+      cudaError_t e = cudaLaunchCooperativeKernel((const void*)k_chol_fused, dim3(grid), dim3(256), args, 0, h->stream);
+      if (e != cudaSuccess) {
+        set_error(h, std::string("cudaLaunchCooperativeKernel(k_chol_fused): ") + cudaGetErrorString(e));
+        return LCBA_E_CUDA;
+      }
+    });
+    if (want_dbg) {
+      long long tmh[6];
+      cudaStreamSynchronize(h->stream);
+      cudaMemcpy(tmh, dbg, sizeof(tmh), cudaMemcpyDeviceToHost);
+      fprintf(stderr, "chol_fused n=%d grid=%d cycles: factor %lld trsm %lld bar1 %lld update %lld bar2 %lld backsub %lld\n",
+              n, grid, tmh[0], tmh[1], tmh[2], tmh[3], tmh[4], tmh[5]);
     }
   }
-  if (h->shared_intr) {
-    KL(h, "chol_solve", k_chol_solve<<<1, 256, (size_t)n * 8, h->stream>>>(h->d_Lf, n, h->d_rhs, h->d_pred));
+  if (h->shared_intr)
     KL(h, "expand", k_expand_shared<<<nblk(h->C * NCP, 128), 128, 0, h->stream>>>(h->d_pred, h->C, h->d_pc));
-  } else {
-    KL(h, "chol_solve", k_chol_solve<<<1, 256, (size_t)n * 8, h->stream>>>(h->d_Lf, n, h->d_rhs, h->d_pc));
-  }
   return check_launch(h, "camera solve");
 }
 
@@ -918,7 +940,7 @@ extern "C" int lcba_solve(lcba_t* h, const lcba_options* opt_in, lcba_result* re
       KL(h, "point_factor", k_point_factor_ctl<<<nblk(h->P, 256), 256, 0, h->stream>>>(
             h->d_Vg, h->d_scl_p, h->d_ctl, h->P, h->d_Lz));
       LCBA_CUDA(h, cudaMemsetAsync(h->d_pc, 0, (size_t)h->C * NCP * 8, h->stream));
-      LCBA_CUDA(h, cudaMemsetAsync(h->d_fail, 0, sizeof(int), h->stream));
+      LCBA_CUDA(h, cudaMemsetAsync(h->d_fail, 0, 2 * sizeof(int), h->stream));
     } else {
       LCBA_TRY(pass_schur(h, nullptr));
     }
@@ -938,6 +960,11 @@ extern "C" int lcba_solve(lcba_t* h, const lcba_options* opt_in, lcba_result* re
         if (g_norm < opt.gtol) status = LCBA_STATUS_GTOL;
         add_trace(h, iteration, nfev, cost, prev_actual, prev_step, g_norm, h->h_ctl->Delta, last_reg);
         if (status >= 0) { gtol_hit = true; break; }
+      }
+      if (h->h_ctl->chol_fail & 2) {
+        set_error(h, "k_chol_fused: grid barrier timed out");
+        cudaEventDestroy(t0); cudaEventDestroy(t1);
+        return LCBA_E_CUDA;
       }
       if (h->h_ctl->retry) {
         mu = std::max(std::max(10.0 * mu, 10.0 * h->h_ctl->reg_term), 1e-13);
