@@ -17,6 +17,7 @@
 #include "ingest.cuh"
 #include "linearize.cuh"
 #include "schur.cuh"
+#include "schur_mma.cuh"
 #include "variants.cuh"
 
 using namespace lcba;
@@ -93,6 +94,12 @@ struct lcba_handle {
   SchurPlan plan;
   SchurKind* d_kinds = nullptr;
   SchurHw* d_hws = nullptr;
+  MmaPlan mplan;                 // tensor-path plan (dense rigs)
+  MmaKind* d_mkinds = nullptr;
+  MmaRegion* d_mregions = nullptr;
+  double *d_U = nullptr, *d_Upart = nullptr;
+  int camn_grid = 0, camn_pb = 0;
+  bool use_mma = false;
   // outputs on demand
   double2* d_rout = nullptr;
   double *d_Jc = nullptr, *d_Jp = nullptr;
@@ -233,7 +240,7 @@ extern "C" int lcba_create(lcba_t** out, int device) {
     const void* big_smem_kernels[] = {(const void*)k_linearize, (const void*)k_backsub,
                                       (const void*)k_schur<true, 160>, (const void*)k_schur<false, 160>,
                                       (const void*)k_schur<true, 128>, (const void*)k_schur<false, 128>,
-                                      (const void*)k_residual,
+                                      (const void*)k_residual, (const void*)k_schur_mma, (const void*)k_cam_normal,
                                       (const void*)k_sq_camonly<true>, (const void*)k_sq_camonly<false>,
                                       (const void*)k_jdot,      (const void*)k_jacobian_blocks};
     for (const void* f : big_smem_kernels) {
@@ -437,9 +444,36 @@ extern "C" int lcba_set_problem_shard(lcba_t* h, int32_t C, int64_t P, int64_t N
   LCBA_CUDA(h, cudaMemcpyAsync(h->d_hws, h->plan.hws.data(), h->plan.hws.size() * sizeof(SchurHw),
                                cudaMemcpyHostToDevice, st));
   LCBA_TRY(dev_alloc(h, &h->d_Sred, h->plan.part_stride));
-  LCBA_TRY(dev_alloc(h, &h->d_Spart, h->plan.part_stride * h->plan.nslices));
+  // tensor-path plan: dense rigs only (the DFMA kernel skips invisible blocks on sparse ones)
+  h->use_mma = false;
+  h->d_mkinds = nullptr; h->d_mregions = nullptr; h->d_U = nullptr; h->d_Upart = nullptr;
+  int max_slices = h->plan.nslices;
+  {
+    const bool dense = (double)N >= 0.8 * (double)P * C;
+    const char* env = getenv("LCBA_SCHUR_MMA");
+    const bool want = env ? atoi(env) != 0 : (dense && C >= 8);
+    if (want) {
+      h->mplan = make_mma_plan(C, h->sm_count, h->smem_optin - 2048);
+      LCBA_TRY(dev_alloc(h, &h->d_mkinds, h->mplan.kinds.size()));
+      LCBA_TRY(dev_alloc(h, &h->d_mregions, h->mplan.regions.size()));
+      LCBA_CUDA(h, cudaMemcpyAsync(h->d_mkinds, h->mplan.kinds.data(), h->mplan.kinds.size() * sizeof(MmaKind),
+                                   cudaMemcpyHostToDevice, st));
+      LCBA_CUDA(h, cudaMemcpyAsync(h->d_mregions, h->mplan.regions.data(),
+                                   h->mplan.regions.size() * sizeof(MmaRegion), cudaMemcpyHostToDevice, st));
+      h->camn_pb = std::max(1, 256 / C);
+      h->camn_grid = (int)std::max<long long>(1, std::min<long long>((P + h->camn_pb - 1) / h->camn_pb,
+                                                                    (long long)h->sm_count));
+      LCBA_TRY(dev_alloc(h, &h->d_Upart, (size_t)h->camn_grid * C * CAMN_VALS));
+      LCBA_TRY(dev_alloc(h, &h->d_U, (size_t)C * CAMN_VALS));
+      max_slices = std::max(max_slices, h->mplan.nslices);
+      h->use_mma = true;
+    }
+  }
+  LCBA_TRY(dev_alloc(h, &h->d_Spart, h->plan.part_stride * max_slices));
   h->d_stats = nullptr;
-  if (getenv("LCBA_SCHUR_STATS")) LCBA_TRY(dev_alloc(h, &h->d_stats, (size_t)h->plan.nslices * h->plan.nkinds * 4));
+  if (getenv("LCBA_SCHUR_STATS"))
+    LCBA_TRY(dev_alloc(h, &h->d_stats, (size_t)std::max(h->plan.nslices * h->plan.nkinds,
+                                                        h->use_mma ? h->mplan.nslices * h->mplan.nkinds : 0) * 4));
   LCBA_CUDA(h, cudaStreamSynchronize(st));
   h->have_problem = true;
   return LCBA_OK;
@@ -692,6 +726,21 @@ static int pass_schur(lcba_t* h, const double* lam_host_or_null) {
     KL(h, "point_factor", k_point_factor_ctl<<<nblk(h->P, 256), 256, 0, h->stream>>>(
           h->d_Vg, h->d_scl_p, h->d_ctl, h->P, h->d_Lz));
   }
+  if (h->use_mma) {
+    // dense rigs: SYRK on the FP64 tensor path + the camera blocks U from their own pass
+    const MmaPlan& mp = h->mplan;
+    const size_t smem_u = ((size_t)((C * CAMTAB + 1) & ~1) + (size_t)h->camn_pb * C) * 8;
+    KL(h, "cam_normal", k_cam_normal<<<h->camn_grid, 256, smem_u, h->stream>>>(
+          h->d_tab[w], h->d_pts[w], h->d_w, h->d_obs_start, h->d_mask, h->P, C, h->camn_pb, h->d_Upart));
+    KL(h, "reduce", k_reduce_cols<<<nblk(C * CAMN_VALS, 128), 128, 0, h->stream>>>(
+          h->d_Upart, h->camn_grid, C * CAMN_VALS, h->d_U));
+    KL(h, "schur", k_schur_mma<<<dim3(mp.nslices, mp.nkinds), MMA_THREADS, mp.smem_bytes, h->stream>>>(
+          h->d_tab[w], h->d_pts[w], h->d_w, h->d_obs_start, h->d_mask, h->d_Lz, h->P, h->N, C,
+          h->d_mkinds, h->d_mregions, mp.nslices, pl.part_stride, pl.npairs, h->d_Spart, h->d_stats));
+    KL(h, "schur_reduce", k_reduce_cols<<<nblk((long long)pl.part_stride, 256), 256, 0, h->stream>>>(
+          h->d_Spart, mp.nslices, (int)pl.part_stride, h->d_Sred));
+    KL(h, "schur_reduce", k_add_cam_blocks<<<nblk(C * 121, 128), 128, 0, h->stream>>>(h->d_U, C, h->d_Sred));
+  } else {
   dim3 grid(pl.nslices, pl.nkinds);
   // sparse rigs skip duo blocks nobody sees; dense rigs run branch-free
   const bool skip = (double)h->N < 0.8 * (double)h->P * C;
@@ -704,6 +753,7 @@ static int pass_schur(lcba_t* h, const double* lam_host_or_null) {
 #undef LCBA_SCHUR_LAUNCH
   KL(h, "schur_reduce", k_reduce_cols<<<nblk((long long)pl.part_stride, 256), 256, 0, h->stream>>>(
         h->d_Spart, pl.nslices, (int)pl.part_stride, h->d_Sred));
+  }
   LCBA_TRY(allreduce(h, h->d_Sred, pl.part_stride, NCCL_SUM));
   if (h->shared_intr) {
     const int nr = 3 + 8 * C;
@@ -1180,10 +1230,12 @@ extern "C" int lcba_comm_init(lcba_t* h, int32_t rank, int32_t nranks, const voi
 // debug: per-CTA cycle counters of the last k_schur launch (LCBA_SCHUR_STATS=1)
 extern "C" int lcba_debug_schur_stats(lcba_t* h, long long* out, int max_ctas, int* nkinds, int* nslices) {
   if (!h || !h->d_stats || !out) return LCBA_E_STATE;
-  const int n = std::min(max_ctas, h->plan.nslices * h->plan.nkinds);
+  const int nk = h->use_mma ? h->mplan.nkinds : h->plan.nkinds;
+  const int ns = h->use_mma ? h->mplan.nslices : h->plan.nslices;
+  const int n = std::min(max_ctas, ns * nk);
   cudaMemcpy(out, h->d_stats, (size_t)n * 4 * sizeof(long long), cudaMemcpyDeviceToHost);
-  *nkinds = h->plan.nkinds;
-  *nslices = h->plan.nslices;
+  *nkinds = nk;
+  *nslices = ns;
   return LCBA_OK;
 }
 
