@@ -96,7 +96,6 @@ struct lcba_handle {
   SchurHw* d_hws = nullptr;
   MmaPlan mplan;                 // tensor-path plan (dense rigs)
   MmaKind* d_mkinds = nullptr;
-  MmaRegion* d_mregions = nullptr;
   double *d_U = nullptr, *d_Upart = nullptr;
   int camn_grid = 0, camn_pb = 0;
   bool use_mma = false;
@@ -240,7 +239,9 @@ extern "C" int lcba_create(lcba_t** out, int device) {
     const void* big_smem_kernels[] = {(const void*)k_linearize, (const void*)k_backsub,
                                       (const void*)k_schur<true, 160>, (const void*)k_schur<false, 160>,
                                       (const void*)k_schur<true, 128>, (const void*)k_schur<false, 128>,
-                                      (const void*)k_residual, (const void*)k_schur_mma, (const void*)k_cam_normal,
+                                      (const void*)k_residual, (const void*)k_cam_normal,
+                                      (const void*)k_schur_mma<1>, (const void*)k_schur_mma<2>, (const void*)k_schur_mma<3>,
+                                      (const void*)k_schur_mma<4>, (const void*)k_schur_mma<5>, (const void*)k_schur_mma<6>,
                                       (const void*)k_sq_camonly<true>, (const void*)k_sq_camonly<false>,
                                       (const void*)k_jdot,      (const void*)k_jacobian_blocks};
     for (const void* f : big_smem_kernels) {
@@ -446,20 +447,17 @@ extern "C" int lcba_set_problem_shard(lcba_t* h, int32_t C, int64_t P, int64_t N
   LCBA_TRY(dev_alloc(h, &h->d_Sred, h->plan.part_stride));
   // tensor-path plan: dense rigs only (the DFMA kernel skips invisible blocks on sparse ones)
   h->use_mma = false;
-  h->d_mkinds = nullptr; h->d_mregions = nullptr; h->d_U = nullptr; h->d_Upart = nullptr;
+  h->d_mkinds = nullptr; h->d_U = nullptr; h->d_Upart = nullptr;
   int max_slices = h->plan.nslices;
   {
     const bool dense = (double)N >= 0.8 * (double)P * C;
     const char* env = getenv("LCBA_SCHUR_MMA");
     const bool want = env ? atoi(env) != 0 : (dense && C >= 8);
-    if (want) {
+    if (want && C <= MMA_MAX_CAMERAS) {
       h->mplan = make_mma_plan(C, h->sm_count, h->smem_optin - 2048);
       LCBA_TRY(dev_alloc(h, &h->d_mkinds, h->mplan.kinds.size()));
-      LCBA_TRY(dev_alloc(h, &h->d_mregions, h->mplan.regions.size()));
       LCBA_CUDA(h, cudaMemcpyAsync(h->d_mkinds, h->mplan.kinds.data(), h->mplan.kinds.size() * sizeof(MmaKind),
                                    cudaMemcpyHostToDevice, st));
-      LCBA_CUDA(h, cudaMemcpyAsync(h->d_mregions, h->mplan.regions.data(),
-                                   h->mplan.regions.size() * sizeof(MmaRegion), cudaMemcpyHostToDevice, st));
       h->camn_pb = std::max(1, 256 / C);
       h->camn_grid = (int)std::max<long long>(1, std::min<long long>((P + h->camn_pb - 1) / h->camn_pb,
                                                                     (long long)h->sm_count));
@@ -734,9 +732,20 @@ static int pass_schur(lcba_t* h, const double* lam_host_or_null) {
           h->d_tab[w], h->d_pts[w], h->d_w, h->d_obs_start, h->d_mask, h->P, C, h->camn_pb, h->d_Upart));
     KL(h, "reduce", k_reduce_cols<<<nblk(C * CAMN_VALS, 128), 128, 0, h->stream>>>(
           h->d_Upart, h->camn_grid, C * CAMN_VALS, h->d_U));
-    KL(h, "schur", k_schur_mma<<<dim3(mp.nslices, mp.nkinds), MMA_THREADS, mp.smem_bytes, h->stream>>>(
-          h->d_tab[w], h->d_pts[w], h->d_w, h->d_obs_start, h->d_mask, h->d_Lz, h->P, h->N, C,
-          h->d_mkinds, h->d_mregions, mp.nslices, pl.part_stride, pl.npairs, h->d_Spart, h->d_stats));
+    const int nt = (NCP * C + 1 + 7) / 8, last = nt - 6 * ((nt + 5) / 6 - 1);
+#define LCBA_MMA_LAUNCH(L)                                                                          \
+  KL(h, "schur", k_schur_mma<L><<<dim3(mp.nslices, mp.nkinds), MMA_THREADS, mp.smem_bytes, h->stream>>>( \
+        h->d_tab[w], h->d_pts[w], h->d_w, h->d_obs_start, h->d_mask, h->d_Lz, h->P, h->N, C,        \
+        h->d_mkinds, mp.nslices, pl.part_stride, pl.npairs, h->d_Spart, h->d_stats))
+    switch (last) {
+      case 1: LCBA_MMA_LAUNCH(1); break;
+      case 2: LCBA_MMA_LAUNCH(2); break;
+      case 3: LCBA_MMA_LAUNCH(3); break;
+      case 4: LCBA_MMA_LAUNCH(4); break;
+      case 5: LCBA_MMA_LAUNCH(5); break;
+      default: LCBA_MMA_LAUNCH(6); break;
+    }
+#undef LCBA_MMA_LAUNCH
     KL(h, "schur_reduce", k_reduce_cols<<<nblk((long long)pl.part_stride, 256), 256, 0, h->stream>>>(
           h->d_Spart, mp.nslices, (int)pl.part_stride, h->d_Sred));
     KL(h, "schur_reduce", k_add_cam_blocks<<<nblk(C * 121, 128), 128, 0, h->stream>>>(h->d_U, C, h->d_Sred));

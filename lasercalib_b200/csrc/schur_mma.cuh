@@ -8,16 +8,20 @@
 // (tools/dmma_syrk.cu, fragment loads included): 33.6 TFLOP/s with one warp per SM
 // sub-partition, 36.9 with two.
 //
-// Decomposition.  Cameras are grouped in quads (4 x 12 padded rows = 48 = 6 tiles of 8); a
-// consumer WARP owns one 48 x 48 region (quad_i x quad_j, j <= i): 36 tiles, 72 FP64
-// accumulators per lane.  A CTA ("kind") holds up to 8 regions = 8 consumer warps + 4 producer
-// warps (register budget moved from the producers to the consumers with setmaxnreg: two
-// consumers and one producer per sub-partition), and streams a slice of the points:
-//   producer: (point, camera slot) -> Y = (Jc^T Jp) L^-T (12 rows: 9 + cx, cy + the z row that
-//             yields the reduced right-hand side, see schur.cuh) into a 2-stage ring laid out
-//             [kappa = 3 q + k][row = 12 slot + r], row stride = 4 (mod 16) doubles, so that the
-//             fragment loads (lane -> row lane/4, kappa lane%4) are conflict free;
-//   consumer: per K-step (4 kappa = 4/3 point) 12 LDS.64 + 36 DMMA.
+// Decomposition.  The matrix that is accumulated is [Y; z] [Y; z]^T with the 11 C rows of Y
+// UNPADDED and one extra row z = L^-1 g_p (its products with Y are the reduced right-hand
+// side): 11 C + 1 rows = nt tiles of 8.  Only tiles on or below the diagonal are computed.
+// Tile rows are grouped by 6; a consumer WARP owns one unit = (row group, column group): a
+// 6 x 6 rectangle of tiles (72 FP64 accumulators per lane), a lower triangle of 21 on the
+// diagonal, smaller at the last group.  Units are packed into CTAs ("kinds") of 8 consumer
+// warps + 4 producer warps, balanced first over the kinds, then over the four SM
+// sub-partitions of a kind (warp w runs on sub-partition w % 4: DMMA time is per
+// sub-partition).  12 warps are launched with 168 registers; the producer warpgroup gives
+// registers back (setmaxnreg.dec 88) and the two consumer warpgroups take them (inc 208).
+//   producer: (point, camera) -> Y = (Jc^T Jp) L^-T (11 rows) into a 2-stage ring laid out
+//             [kappa = 3 q + k][12 c + r | z 0 0 0], row stride = 4 (mod 16) doubles, so that
+//             the fragment loads (lane -> row lane/4, kappa lane%4) are conflict free;
+//   consumer: per K-step (4 kappa = 4/3 point) <= 12 LDS.64 + <= 36 DMMA.
 // Invisible (point, camera) pairs and the tail of the last chunk are exact zeros.  The
 // camera blocks U_j = sum Jc^T Jc are accumulated by k_cam_normal (one thread per (point,
 // camera), fixed camera per thread, 66 register accumulators) and added to the diagonal pair
@@ -30,111 +34,84 @@
 
 namespace lcba {
 
-constexpr int MMA_REGIONS = 8;        // consumer warps per CTA (two warpgroups)
+constexpr int MMA_CONS_WARPS = 8;     // consumer warps per CTA (two warpgroups)
 constexpr int MMA_PROD_WARPS = 4;     // producer warps (one warpgroup)
-constexpr int MMA_THREADS = 32 * (MMA_REGIONS + MMA_PROD_WARPS);
-// 12 warps are launched with 168 registers each; the producer warpgroup gives registers back
-// (setmaxnreg.dec) and the two consumer warpgroups take them (setmaxnreg.inc): every SM
-// sub-partition then holds 2 consumer warps x 208 + 1 producer warp x 88 registers.
+constexpr int MMA_THREADS = 32 * (MMA_CONS_WARPS + MMA_PROD_WARPS);
+constexpr int MMA_MAX_CAMERAS = 32;   // every kind stages all cameras: beyond this the DFMA kernel
 #define MMA_CONS_REGS "208"
 #define MMA_PROD_REGS "88"
 
-struct MmaRegion {
-  int8_t srow[4], scol[4];   // shared-memory slots of the row / column cameras (0 when absent)
-  int8_t crow[4], ccol[4];   // camera ids or -1
+struct MmaUnit {          // tile rectangle [tr0, tr0 + nr) x [tc0, tc0 + nc); nr = 0: idle warp
+  int16_t tr0, tc0;
+  int8_t nr, nc, tri, pad;
 };
 
 struct MmaKind {
-  int nslots, nreg, reg_base, rp;   // rp: row stride of the ring in doubles (= 4 mod 16)
-  int sp, pad0, pad1, pad2;         // points per stage (multiple of 4)
-  uint8_t slot_cam[LCBA_MAX_CAMERAS];
+  int nactive, rp, sp, pad0;            // active consumer warps; ring row stride; points per stage
+  MmaUnit unit[MMA_CONS_WARPS];
 };
 
 struct MmaPlan {
   int C = 0, nkinds = 0, nslices = 0;
   size_t smem_bytes = 0;
   std::vector<MmaKind> kinds;
-  std::vector<MmaRegion> regions;
 };
 
 inline MmaPlan make_mma_plan(int C, int sm_count, size_t smem_limit) {
   MmaPlan pl;
   pl.C = C;
-  const int nq = (C + 3) / 4;
-  std::vector<std::vector<char>> freeb(nq, std::vector<char>(nq, 0));
-  size_t nfree = 0;
-  for (int j = 0; j < nq; ++j)
-    for (int k = 0; k <= j; ++k) { freeb[j][k] = 1; ++nfree; }
-  // same greedy clustering as the duo plan: a kind keeps a quad set D, takes the free regions
-  // inside D x D and grows D by the quad that unlocks the most free regions; regions are spread
-  // evenly over the minimum number of kinds (24 cameras: 21 regions = 3 kinds x 7)
-  const int nk_min = (int)((nfree + MMA_REGIONS - 1) / MMA_REGIONS);
-  const int cap = (int)((nfree + nk_min - 1) / nk_min);
-  while (nfree > 0) {
+  const int nrows = NCP * C + 1, nt = (nrows + 7) / 8, ng = (nt + 5) / 6;
+  struct U { MmaUnit u; int cost; };
+  std::vector<U> units;
+  long long total = 0;
+  for (int gi = 0; gi < ng; ++gi)
+    for (int gj = 0; gj <= gi; ++gj) {
+      U x{};
+      x.u.tr0 = (int16_t)(6 * gi);
+      x.u.tc0 = (int16_t)(6 * gj);
+      x.u.nr = (int8_t)std::min(6, nt - 6 * gi);
+      x.u.nc = (int8_t)std::min(6, nt - 6 * gj);
+      x.u.tri = gi == gj;
+      x.cost = x.u.tri ? x.u.nr * (x.u.nr + 1) / 2 : x.u.nr * x.u.nc;
+      total += x.cost;
+      units.push_back(x);
+    }
+  std::sort(units.begin(), units.end(), [](const U& a, const U& b) { return a.cost > b.cost; });
+  const int nk = (int)((units.size() + MMA_CONS_WARPS - 1) / MMA_CONS_WARPS);
+  std::vector<std::vector<U>> per_kind(nk);
+  std::vector<long long> kcost(nk, 0);
+  for (const U& x : units) {   // longest processing time first, into the lightest kind with room
+    int best = -1;
+    for (int k = 0; k < nk; ++k)
+      if ((int)per_kind[k].size() < MMA_CONS_WARPS && (best < 0 || kcost[k] < kcost[best])) best = k;
+    per_kind[best].push_back(x);
+    kcost[best] += x.cost;
+  }
+  int rp = C * 12 + 2;
+  while (rp % 16 != 4) ++rp;
+  const size_t fixed = (size_t)C * CAMTAB * 8 + 64;
+  int sp = (int)((smem_limit - fixed) / ((size_t)3 * rp * 8 * SCHUR_STAGES));
+  sp = std::max(4, std::min(16, sp / 4 * 4));
+  pl.smem_bytes = (size_t)3 * sp * rp * 8 * SCHUR_STAGES + fixed;
+  for (int k = 0; k < nk; ++k) {
     MmaKind K{};
-    K.reg_base = (int)pl.regions.size();
-    std::vector<char> inD(nq, 0);
-    std::vector<std::pair<int, int>> blks;
-    while (nfree > 0 && (int)blks.size() < cap) {
-      int bj = -1, bk = -1;
-      for (int j = 0; j < nq && bj < 0; ++j) {
-        if (!inD[j]) continue;
-        for (int k = 0; k <= j; ++k)
-          if (inD[k] && freeb[j][k]) { bj = j; bk = k; break; }
-      }
-      if (bj < 0) {
-        int best = -1, gain_best = 0;
-        for (int d = 0; d < nq; ++d) {
-          if (inD[d]) continue;
-          int gain = freeb[d][d] ? 1 : 0;
-          for (int x = 0; x < nq; ++x)
-            if (inD[x]) gain += (x < d) ? freeb[d][x] : freeb[x][d];
-          if (gain > gain_best) { gain_best = gain; best = d; }
-        }
-        if (best < 0) {
-          for (int j = 0; j < nq && best < 0; ++j)
-            for (int k = 0; k <= j; ++k)
-              if (freeb[j][k]) { inD[j] = 1; inD[k] = 1; best = j; break; }
-        } else {
-          inD[best] = 1;
-        }
-        continue;
-      }
-      freeb[bj][bk] = 0;
-      --nfree;
-      blks.push_back({bj, bk});
+    K.rp = rp;
+    K.sp = sp;
+    // units of the kind over the sub-partitions (2 warp slots each): lightest one with room
+    long long load[4] = {0, 0, 0, 0};
+    int used[4] = {0, 0, 0, 0};
+    for (const U& x : per_kind[k]) {   // already sorted by decreasing cost
+      int best = -1;
+      for (int q = 0; q < 4; ++q)
+        if (used[q] < 2 && (best < 0 || load[q] < load[best])) best = q;
+      K.unit[best + 4 * used[best]] = x.u;
+      load[best] += x.cost;
+      ++used[best];
+      ++K.nactive;
     }
-    bool used[LCBA_MAX_CAMERAS] = {false};
-    for (auto& bl : blks)
-      for (int d = 0; d < 4; ++d) {
-        if (4 * bl.first + d < C) used[4 * bl.first + d] = true;
-        if (4 * bl.second + d < C) used[4 * bl.second + d] = true;
-      }
-    int slot_of[LCBA_MAX_CAMERAS];
-    for (int c = 0; c < C; ++c)
-      if (used[c]) { slot_of[c] = K.nslots; K.slot_cam[K.nslots++] = (uint8_t)c; }
-    for (auto& bl : blks) {
-      MmaRegion r{};
-      for (int d = 0; d < 4; ++d) {
-        const int cr = 4 * bl.first + d, cc = 4 * bl.second + d;
-        r.crow[d] = (int8_t)(cr < C ? cr : -1);
-        r.srow[d] = (int8_t)(cr < C ? slot_of[cr] : 0);
-        r.ccol[d] = (int8_t)(cc < C ? cc : -1);
-        r.scol[d] = (int8_t)(cc < C ? slot_of[cc] : 0);
-      }
-      pl.regions.push_back(r);
-    }
-    K.nreg = (int)blks.size();
-    K.rp = K.nslots * 12;
-    while (K.rp % 16 != 4) ++K.rp;
-    const size_t fixed = (size_t)C * CAMTAB * 8 + 64;
-    int sp = (int)((smem_limit - fixed) / ((size_t)3 * K.rp * 8 * SCHUR_STAGES));
-    sp = std::min(16, sp / 4 * 4);
-    K.sp = std::max(4, sp);
-    pl.smem_bytes = std::max(pl.smem_bytes, (size_t)3 * K.sp * K.rp * 8 * SCHUR_STAGES + fixed);
     pl.kinds.push_back(K);
   }
-  pl.nkinds = (int)pl.kinds.size();
+  pl.nkinds = nk;
   pl.nslices = std::max(1, sm_count / pl.nkinds);
   return pl;
 }
@@ -168,28 +145,99 @@ __device__ __forceinline__ void mma_produce(const double* __restrict__ T, const 
     o[2] = make_double2(y[4], y[5]);
     o[3] = make_double2(y[6], y[7]);
     o[4] = make_double2(y[8], w * Q[0][k]);
-    o[5] = make_double2(w * Q[1][k], li[6 + k]);      // row 11 = z: rhs for free (schur.cuh)
+    o[5] = make_double2(w * Q[1][k], 0.0);
+  }
+}
+
+// Ring offset of matrix row rho: camera rows are stored with stride 12, then z, then zeros.
+__device__ __forceinline__ int mma_row_offset(int rho, int C) {
+  const int n = NCP * C;
+  if (rho < n) return (rho / NCP) * 12 + rho % NCP;
+  return C * 12 + (rho == n ? 0 : 1);
+}
+
+// Consumer body for one unit shape (NR x NC tiles, TRI: lower triangle): everything static,
+// the DMMA stream is branch free.
+template <int NR, int NC, bool TRI>
+__device__ __forceinline__ void mma_consume(const MmaUnit& U, const double* s_dyn, size_t stage_doubles,
+                                            int rp, int ksteps, long long nchunks, int nthreads,
+                                            int bar_full, int bar_empty, int C, int lane,
+                                            double* __restrict__ out, double* __restrict__ rout) {
+  int offA[NR], offB[NC];
+#pragma unroll
+  for (int t = 0; t < NR; ++t) offA[t] = mma_row_offset(8 * (U.tr0 + t) + (lane >> 2), C) + (lane & 3) * rp;
+#pragma unroll
+  for (int u = 0; u < NC; ++u) offB[u] = mma_row_offset(8 * (U.tc0 + u) + (lane >> 2), C) + (lane & 3) * rp;
+  double acc[NR][NC][2];
+#pragma unroll
+  for (int t = 0; t < NR; ++t)
+#pragma unroll
+    for (int u = 0; u < NC; ++u) acc[t][u][0] = acc[t][u][1] = 0.0;
+  for (long long c = 0; c < nchunks; ++c) {
+    const int st = (int)(c % SCHUR_STAGES);
+    const double* s_Y = s_dyn + st * stage_doubles;
+    nbar_sync(bar_full + st, nthreads);
+#pragma unroll 1
+    for (int ks = 0; ks < ksteps; ++ks) {
+      const double* base = s_Y + (size_t)ks * 4 * rp;
+      double a[NR], b[NC];
+#pragma unroll
+      for (int t = 0; t < NR; ++t) a[t] = base[offA[t]];
+#pragma unroll
+      for (int u = 0; u < NC; ++u) b[u] = base[offB[u]];
+#pragma unroll
+      for (int t = 0; t < NR; ++t)
+#pragma unroll
+        for (int u = 0; u < NC; ++u)
+          if (!TRI || u <= t) dmma884(acc[t][u], a[t], b[u]);
+    }
+    nbar_arrive(bar_empty + st, nthreads);
+  }
+  // slice partial: every lower-triangle pair entry exactly once (same-camera blocks are stored
+  // with both triangles: the mirror is written alongside)
+  const int n = NCP * C;
+#pragma unroll
+  for (int t = 0; t < NR; ++t) {
+    const int rho = 8 * (U.tr0 + t) + (lane >> 2);
+    if (rho > n) continue;
+#pragma unroll
+    for (int u = 0; u < NC; ++u) {
+      if (TRI && u > t) continue;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int sig = 8 * (U.tc0 + u) + 2 * (lane & 3) + e;
+        if (sig >= n || sig > rho) continue;
+        const double v = -acc[t][u][e];
+        const int ck = sig / NCP, cb = sig % NCP;
+        if (rho == n) { rout[ck * NCP + cb] = v; continue; }          // z row: reduced rhs
+        const int cj = rho / NCP, ra = rho % NCP;
+        double* blk = out + (size_t)(cj * (cj + 1) / 2 + ck) * 121;
+        blk[ra * NCP + cb] = v;
+        if (cj == ck && ra != cb) blk[cb * NCP + ra] = v;
+      }
+    }
   }
 }
 
 // part[slice][npairs*121 + 11 C]: - sum Y Y^T per pair block (11 x 11) and the reduced rhs.
+// LAST = number of tile rows of the last group (compile time, so that every unit shape is).
+template <int LAST>
 __global__ void __launch_bounds__(MMA_THREADS, 1)
 k_schur_mma(const double* __restrict__ tab, const double* __restrict__ pts,
             const double* __restrict__ wgt, const uint32_t* __restrict__ obs_start,
             const unsigned long long* __restrict__ mask, const double* __restrict__ Lz,
-            long long P, long long N, int C, const MmaKind* __restrict__ kinds,
-            const MmaRegion* __restrict__ regions, int nslices, size_t part_stride, int npairs,
-            double* __restrict__ part, long long* __restrict__ stats) {
+            long long P, long long N, int C, const MmaKind* __restrict__ kinds, int nslices,
+            size_t part_stride, int npairs, double* __restrict__ part,
+            long long* __restrict__ stats) {
   extern __shared__ __align__(16) double s_dyn[];
   const MmaKind& K = kinds[blockIdx.y];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int nreg = K.nreg, nthreads = 32 * (nreg + MMA_PROD_WARPS);   // barrier participants
-  const int nslots = K.nslots, SP = K.sp, rp = K.rp;
+  const int nthreads = 32 * (K.nactive + MMA_PROD_WARPS);   // barrier participants
+  const int SP = K.sp, rp = K.rp;
   const size_t stage_doubles = (size_t)3 * SP * rp;
   double* s_tab = s_dyn + SCHUR_STAGES * stage_doubles;
   enum { BAR_FULL = 2, BAR_EMPTY = BAR_FULL + SCHUR_STAGES, BAR_PROD = BAR_EMPTY + SCHUR_STAGES };
   const long long t_start = clock64();
-  long long t_wait = 0;
 
   const int slice = blockIdx.x;
   long long pa, pb;
@@ -201,23 +249,34 @@ k_schur_mma(const double* __restrict__ tab, const double* __restrict__ pts,
   }
   const long long nchunks = (pb - pa + SP - 1) / SP;
 
-  if (wid >= MMA_REGIONS) {
+  if (wid >= MMA_CONS_WARPS) {
     // ================================ producer warpgroup ================================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 " MMA_PROD_REGS ";");
-    const int ptid = tid - 32 * MMA_REGIONS, nprod = 32 * MMA_PROD_WARPS;
+    const int ptid = tid - 32 * MMA_CONS_WARPS, nprod = 32 * MMA_PROD_WARPS;
     for (int i = ptid; i < C * CAMTAB; i += nprod) s_tab[i] = tab[i];
     nbar_sync(BAR_PROD, nprod);
-    const int total = SP * nslots;
+    const int total = SP * C;
     for (long long c = 0; c < nchunks + SCHUR_STAGES; ++c) {
       const int st = (int)(c % SCHUR_STAGES);
-      if (c >= SCHUR_STAGES) { const long long t0 = clock64(); nbar_sync(BAR_EMPTY + st, nthreads); t_wait += clock64() - t0; }
+      if (c >= SCHUR_STAGES) nbar_sync(BAR_EMPTY + st, nthreads);
       if (c >= nchunks) continue;
       double* s_Y = s_dyn + st * stage_doubles;
       const long long q0 = pa + c * SP;
-      for (int idx = ptid; idx < total; idx += nprod) {
-        const int q = idx / nslots, sl = idx - q * nslots;
+      for (int idx = ptid; idx < total + SP; idx += nprod) {
+        if (idx >= total) {   // the z row of point q (and the zero row behind it)
+          const int q = idx - total;
+          const long long p = q0 + q;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            double* o = s_Y + (size_t)(3 * q + k) * rp + C * 12;
+            o[0] = (p < pb) ? Lz[p * 9 + 6 + k] : 0.0;
+            o[1] = 0.0;
+          }
+          continue;
+        }
+        const int q = idx / C, cam = idx - q * C;
         const long long p = q0 + q;
-        double* Yk0 = s_Y + (size_t)3 * q * rp + sl * 12;
+        double* Yk0 = s_Y + (size_t)3 * q * rp + cam * 12;
         if (p >= pb) {
 #pragma unroll
           for (int k = 0; k < 3; ++k) {
@@ -228,7 +287,6 @@ k_schur_mma(const double* __restrict__ tab, const double* __restrict__ pts,
           continue;
         }
         const unsigned long long m = mask[p];
-        const int cam = K.slot_cam[sl];
         const bool live = (m >> cam) & 1ull;
         double w = 0.0;
         if (live) w = wgt ? wgt[(long long)obs_start[p] + __popcll(m & ((1ull << cam) - 1ull))] : 1.0;
@@ -244,7 +302,7 @@ k_schur_mma(const double* __restrict__ tab, const double* __restrict__ pts,
     }
     if (stats && ptid == 0) {
       long long* o = stats + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 4;
-      o[2] = t_wait;
+      o[2] = 0;
       o[3] = clock64() - t_start;
     }
     return;
@@ -252,63 +310,21 @@ k_schur_mma(const double* __restrict__ tab, const double* __restrict__ pts,
 
   // ================================ consumer warpgroups ================================
   asm volatile("setmaxnreg.inc.sync.aligned.u32 " MMA_CONS_REGS ";");
-  if (wid >= nreg) return;                           // no region for this warp in this kind
-  const MmaRegion R = regions[K.reg_base + wid];
-  int offA[6], offB[6];
-#pragma unroll
-  for (int t = 0; t < 6; ++t) {
-    const int rho = 8 * t + (lane >> 2);
-    offA[t] = R.srow[rho / 12] * 12 + rho % 12 + (lane & 3) * rp;
-    offB[t] = R.scol[rho / 12] * 12 + rho % 12 + (lane & 3) * rp;
-  }
-  double acc[6][6][2];
-#pragma unroll
-  for (int t = 0; t < 6; ++t)
-#pragma unroll
-    for (int u = 0; u < 6; ++u) acc[t][u][0] = acc[t][u][1] = 0.0;
-
-  const int ksteps = 3 * SP / 4;
-  for (long long c = 0; c < nchunks; ++c) {
-    const int st = (int)(c % SCHUR_STAGES);
-    const double* s_Y = s_dyn + st * stage_doubles;
-    { const long long t0 = clock64(); nbar_sync(BAR_FULL + st, nthreads); t_wait += clock64() - t0; }
-#pragma unroll 1
-    for (int ks = 0; ks < ksteps; ++ks) {
-      const double* base = s_Y + (size_t)ks * 4 * rp;
-      double a[6], b[6];
-#pragma unroll
-      for (int t = 0; t < 6; ++t) { a[t] = base[offA[t]]; b[t] = base[offB[t]]; }
-#pragma unroll
-      for (int t = 0; t < 6; ++t)
-#pragma unroll
-        for (int u = 0; u < 6; ++u) dmma884(acc[t][u], a[t], b[u]);
-    }
-    nbar_arrive(BAR_EMPTY + st, nthreads);
-  }
-  if (stats && tid == 0) {
-    long long* o = stats + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 4;
-    o[0] = t_wait;
-    o[1] = clock64() - t_start;
-  }
-  // ---------------- slice partial: every lower-triangle pair entry exactly once ----------------
+  const MmaUnit U = K.unit[wid];
+  if (U.nr == 0) return;                             // idle warp slot of this kind
   double* out = part + (size_t)slice * part_stride;
   double* rout = out + (size_t)npairs * 121;
-#pragma unroll
-  for (int t = 0; t < 6; ++t) {
-    const int rho = 8 * t + (lane >> 2);
-    const int cj = R.crow[rho / 12], ra = rho % 12;
-    if (cj < 0 || ra >= NCP) continue;
-#pragma unroll
-    for (int u = 0; u < 6; ++u) {
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int sig = 8 * u + 2 * (lane & 3) + e;
-        const int ck = R.ccol[sig / 12], cb = sig % 12;
-        if (ck < 0 || ck > cj) continue;
-        if (cb < NCP) out[(size_t)(cj * (cj + 1) / 2 + ck) * 121 + ra * NCP + cb] = -acc[t][u][e];
-        else if (ck == cj) rout[cj * NCP + ra] = -acc[t][u][e];
-      }
-    }
+  const int ksteps = 3 * SP / 4;
+#define MMA_CONSUME(NR, NC, TRI)                                                                   \
+  mma_consume<NR, NC, TRI>(U, s_dyn, stage_doubles, rp, ksteps, nchunks, nthreads, BAR_FULL, BAR_EMPTY, \
+                           C, lane, out, rout)
+  if (U.nr == 6) { if (U.tri) MMA_CONSUME(6, 6, true); else MMA_CONSUME(6, 6, false); }
+  else           { if (U.tri) MMA_CONSUME(LAST, LAST, true); else MMA_CONSUME(LAST, 6, false); }
+#undef MMA_CONSUME
+  if (stats && lane == 0 && wid == 0) {
+    long long* o = stats + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 4;
+    o[0] = 0;
+    o[1] = clock64() - t_start;
   }
 }
 
