@@ -76,8 +76,20 @@ inline MmaPlan make_mma_plan(int C, int sm_count, size_t smem_limit) {
       total += x.cost;
       units.push_back(x);
     }
-  std::sort(units.begin(), units.end(), [](const U& a, const U& b) { return a.cost > b.cost; });
   const int nk = (int)((units.size() + MMA_CONS_WARPS - 1) / MMA_CONS_WARPS);
+  // spare warp slots: split full 6 x 6 units into two 3 x 6 halves (finer grain for the balance
+  // over the sub-partitions; 24 cameras: max load 54 tiles instead of 60)
+  for (size_t i = 0; i < units.size() && (int)units.size() < nk * MMA_CONS_WARPS; ++i) {
+    if (units[i].u.tri || units[i].u.nr != 6 || units[i].u.nc != 6) continue;
+    U lo = units[i];
+    lo.u.nr = 3;
+    lo.cost = 18;
+    U hi = lo;
+    hi.u.tr0 = (int16_t)(lo.u.tr0 + 3);
+    units[i] = lo;
+    units.push_back(hi);
+  }
+  std::sort(units.begin(), units.end(), [](const U& a, const U& b) { return a.cost > b.cost; });
   std::vector<std::vector<U>> per_kind(nk);
   std::vector<long long> kcost(nk, 0);
   for (const U& x : units) {   // longest processing time first, into the lightest kind with room
@@ -318,8 +330,9 @@ k_schur_mma(const double* __restrict__ tab, const double* __restrict__ pts,
 #define MMA_CONSUME(NR, NC, TRI)                                                                   \
   mma_consume<NR, NC, TRI>(U, s_dyn, stage_doubles, rp, ksteps, nchunks, nthreads, BAR_FULL, BAR_EMPTY, \
                            C, lane, out, rout)
-  if (U.nr == 6) { if (U.tri) MMA_CONSUME(6, 6, true); else MMA_CONSUME(6, 6, false); }
-  else           { if (U.tri) MMA_CONSUME(LAST, LAST, true); else MMA_CONSUME(LAST, 6, false); }
+  if (U.nr == 6)                { if (U.tri) MMA_CONSUME(6, 6, true); else MMA_CONSUME(6, 6, false); }
+  else if (U.nr == 3 && !U.tri) MMA_CONSUME(3, 6, false);            // half of a split 6 x 6 unit
+  else                          { if (U.tri) MMA_CONSUME(LAST, LAST, true); else MMA_CONSUME(LAST, 6, false); }
 #undef MMA_CONSUME
   if (stats && lane == 0 && wid == 0) {
     long long* o = stats + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 4;
