@@ -99,6 +99,7 @@ struct lcba_handle {
   double *d_U = nullptr, *d_Upart = nullptr;
   int camn_grid = 0, camn_pb = 0;
   bool use_mma = false;
+  double* d_Yg = nullptr;        // Y of every (point, camera) in ring layout (k_make_Y), or null
   // outputs on demand
   double2* d_rout = nullptr;
   double *d_Jc = nullptr, *d_Jp = nullptr;
@@ -239,9 +240,13 @@ extern "C" int lcba_create(lcba_t** out, int device) {
     const void* big_smem_kernels[] = {(const void*)k_linearize, (const void*)k_backsub,
                                       (const void*)k_schur<true, 160>, (const void*)k_schur<false, 160>,
                                       (const void*)k_schur<true, 128>, (const void*)k_schur<false, 128>,
-                                      (const void*)k_residual, (const void*)k_cam_normal,
-                                      (const void*)k_schur_mma<1>, (const void*)k_schur_mma<2>, (const void*)k_schur_mma<3>,
-                                      (const void*)k_schur_mma<4>, (const void*)k_schur_mma<5>, (const void*)k_schur_mma<6>,
+                                      (const void*)k_residual, (const void*)k_cam_normal, (const void*)k_make_Y,
+                                      (const void*)k_schur_mma<1, false>, (const void*)k_schur_mma<2, false>,
+                                      (const void*)k_schur_mma<3, false>, (const void*)k_schur_mma<4, false>,
+                                      (const void*)k_schur_mma<5, false>, (const void*)k_schur_mma<6, false>,
+                                      (const void*)k_schur_mma<1, true>, (const void*)k_schur_mma<2, true>,
+                                      (const void*)k_schur_mma<3, true>, (const void*)k_schur_mma<4, true>,
+                                      (const void*)k_schur_mma<5, true>, (const void*)k_schur_mma<6, true>,
                                       (const void*)k_sq_camonly<true>, (const void*)k_sq_camonly<false>,
                                       (const void*)k_jdot,      (const void*)k_jacobian_blocks};
     for (const void* f : big_smem_kernels) {
@@ -447,7 +452,7 @@ extern "C" int lcba_set_problem_shard(lcba_t* h, int32_t C, int64_t P, int64_t N
   LCBA_TRY(dev_alloc(h, &h->d_Sred, h->plan.part_stride));
   // tensor-path plan: dense rigs only (the DFMA kernel skips invisible blocks on sparse ones)
   h->use_mma = false;
-  h->d_mkinds = nullptr; h->d_U = nullptr; h->d_Upart = nullptr;
+  h->d_mkinds = nullptr; h->d_U = nullptr; h->d_Upart = nullptr; h->d_Yg = nullptr;
   int max_slices = h->plan.nslices;
   {
     const bool dense = (double)N >= 0.8 * (double)P * C;
@@ -465,6 +470,15 @@ extern "C" int lcba_set_problem_shard(lcba_t* h, int32_t C, int64_t P, int64_t N
       LCBA_TRY(dev_alloc(h, &h->d_U, (size_t)C * CAMN_VALS));
       max_slices = std::max(max_slices, h->mplan.nslices);
       h->use_mma = true;
+      // Y precomputed in HBM when it fits comfortably (288 B per (point, camera)); otherwise the
+      // producers of k_schur_mma evaluate it in place
+      {
+        const size_t need = (size_t)(P + 1) * 3 * h->mplan.kinds[0].rp * 8;
+        size_t fr = 0, tot = 0;
+        const char* pe = getenv("LCBA_MMA_PRE");
+        if (cudaMemGetInfo(&fr, &tot) == cudaSuccess && need < fr / 3 && !(pe && atoi(pe) == 0))
+          LCBA_TRY(dev_alloc(h, &h->d_Yg, need / 8));
+      }
     }
   }
   LCBA_TRY(dev_alloc(h, &h->d_Spart, h->plan.part_stride * max_slices));
@@ -733,10 +747,25 @@ static int pass_schur(lcba_t* h, const double* lam_host_or_null) {
     KL(h, "reduce", k_reduce_cols<<<nblk(C * CAMN_VALS, 128), 128, 0, h->stream>>>(
           h->d_Upart, h->camn_grid, C * CAMN_VALS, h->d_U));
     const int nt = (NCP * C + 1 + 7) / 8, last = nt - 6 * ((nt + 5) / 6 - 1);
+    if (h->d_Yg) {
+      const int pbk = MAKEY_THREADS / C, rpk = mp.kinds[0].rp;
+      const size_t smem_y = ((size_t)((C * CAMTAB + 1) & ~1) + (size_t)3 * pbk * rpk) * 8;
+      const int grid_y = (int)std::min<long long>((h->P + pbk - 1) / pbk, (long long)h->sm_count * 5);
+      KL(h, "make_Y", k_make_Y<<<grid_y, MAKEY_THREADS, smem_y, h->stream>>>(
+            h->d_tab[w], h->d_pts[w], h->d_w, h->d_obs_start, h->d_mask, h->d_Lz, h->P, C, mp.kinds[0].rp,
+            h->d_Yg));
+    }
 #define LCBA_MMA_LAUNCH(L)                                                                          \
-  KL(h, "schur", k_schur_mma<L><<<dim3(mp.nslices, mp.nkinds), MMA_THREADS, mp.smem_bytes, h->stream>>>( \
-        h->d_tab[w], h->d_pts[w], h->d_w, h->d_obs_start, h->d_mask, h->d_Lz, h->P, h->N, C,        \
-        h->d_mkinds, mp.nslices, pl.part_stride, pl.npairs, h->d_Spart, h->d_stats))
+  do {                                                                                              \
+    if (h->d_Yg)                                                                                    \
+      KL(h, "schur", (k_schur_mma<L, true><<<dim3(mp.nslices, mp.nkinds), MMA_THREADS, mp.smem_bytes, h->stream>>>( \
+            h->d_Yg, h->d_tab[w], h->d_pts[w], h->d_w, h->d_obs_start, h->d_mask, h->d_Lz, h->P, h->N, C, \
+            h->d_mkinds, mp.nslices, pl.part_stride, pl.npairs, h->d_Spart, h->d_stats)));          \
+    else                                                                                            \
+      KL(h, "schur", (k_schur_mma<L, false><<<dim3(mp.nslices, mp.nkinds), MMA_THREADS, mp.smem_bytes, h->stream>>>( \
+            nullptr, h->d_tab[w], h->d_pts[w], h->d_w, h->d_obs_start, h->d_mask, h->d_Lz, h->P, h->N, C, \
+            h->d_mkinds, mp.nslices, pl.part_stride, pl.npairs, h->d_Spart, h->d_stats)));          \
+  } while (0)
     switch (last) {
       case 1: LCBA_MMA_LAUNCH(1); break;
       case 2: LCBA_MMA_LAUNCH(2); break;

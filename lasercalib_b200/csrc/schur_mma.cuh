@@ -168,6 +168,69 @@ __device__ __forceinline__ int mma_row_offset(int rho, int C) {
   return C * 12 + (rho == n ? 0 : 1);
 }
 
+// ---- Y precomputed in HBM ------------------------------------------------------------------
+// Inside k_schur_mma the producers' FP64 instructions have to squeeze in between the DMMAs of
+// two consumer warps per sub-partition: every dependent step of the ~200-instruction Jacobian
+// chain waits for a pipe slot and the producers, not the tensor pipe, set the pace (ncu: 29 %
+// barrier stalls, tensor pipe 53 % active).  k_make_Y therefore evaluates Y once per iteration
+// at full occupancy and stores it in exactly the ring layout ([point][kappa][rp] doubles, z
+// and the zero column included): the producers of every kind then only copy contiguous rows
+// with cp.async (no FP64 work, no registers).  Costs 288 B per (point, camera) of HBM write
+// and nkinds reads; the Schur pass is compute bound, HBM is idle otherwise.
+// Block = 128 / C points at a time (small blocks: several per SM overlap their two phases): thread (camera t % C, point t / C) evaluates its item into a
+// shared-memory tile that has the global layout, then the whole tile (contiguous in Yg) is
+// written with coalesced 16-byte stores.
+constexpr int MAKEY_THREADS = 128;
+__global__ void __launch_bounds__(MAKEY_THREADS)
+k_make_Y(const double* __restrict__ tab, const double* __restrict__ pts,
+         const double* __restrict__ wgt, const uint32_t* __restrict__ obs_start,
+         const unsigned long long* __restrict__ mask, const double* __restrict__ Lz, long long P,
+         int C, int rp, double* __restrict__ Yg) {
+  extern __shared__ __align__(16) double s_dyn[];
+  double* s_tab = s_dyn;
+  double* tile = s_dyn + ((C * CAMTAB + 1) & ~1);          // [3 * PB][rp]
+  const int t = threadIdx.x, PB = MAKEY_THREADS / C;
+  load_tables_smem(tab, s_tab, C);
+  __syncthreads();
+  const int cam = t % C, pl = t / C;
+  for (long long p0 = (long long)blockIdx.x * PB; p0 < P; p0 += (long long)gridDim.x * PB) {
+    const int npts = (int)min((long long)PB, P - p0);
+    if (pl < npts) {
+      const long long p = p0 + pl;
+      const unsigned long long m = mask[p];
+      const bool live = (m >> cam) & 1ull;
+      double w = 0.0;
+      if (live) w = wgt ? wgt[(long long)obs_start[p] + __popcll(m & ((1ull << cam) - 1ull))] : 1.0;
+      double X[3], li[9];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) X[a] = pts[3 * p + a];
+#pragma unroll
+      for (int a = 0; a < 9; ++a) li[a] = Lz[p * 9 + a];
+      double* row0 = tile + (size_t)3 * pl * rp;
+      mma_produce(s_tab + cam * CAMTAB, X, li, w, live, row0 + cam * 12, rp);
+      if (cam == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          double* o = row0 + (size_t)k * rp + C * 12;
+          o[0] = li[6 + k];
+          for (int e = 1; e < rp - C * 12; ++e) o[e] = 0.0;
+        }
+      }
+    }
+    __syncthreads();
+    const int n2 = 3 * npts * rp / 2;
+    double2* dst = reinterpret_cast<double2*>(Yg + (size_t)p0 * 3 * rp);
+    const double2* src = reinterpret_cast<const double2*>(tile);
+    for (int i = t; i < n2; i += MAKEY_THREADS) dst[i] = src[i];
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+
 // Consumer body for one unit shape (NR x NC tiles, TRI: lower triangle): everything static,
 // the DMMA stream is branch free.
 template <int NR, int NC, bool TRI>
@@ -233,9 +296,10 @@ __device__ __forceinline__ void mma_consume(const MmaUnit& U, const double* s_dy
 
 // part[slice][npairs*121 + 11 C]: - sum Y Y^T per pair block (11 x 11) and the reduced rhs.
 // LAST = number of tile rows of the last group (compile time, so that every unit shape is).
-template <int LAST>
+// PRE: Y comes from k_make_Y (Yg), the producers only copy; otherwise they evaluate it in place.
+template <int LAST, bool PRE>
 __global__ void __launch_bounds__(MMA_THREADS, 1)
-k_schur_mma(const double* __restrict__ tab, const double* __restrict__ pts,
+k_schur_mma(const double* __restrict__ Yg, const double* __restrict__ tab, const double* __restrict__ pts,
             const double* __restrict__ wgt, const uint32_t* __restrict__ obs_start,
             const unsigned long long* __restrict__ mask, const double* __restrict__ Lz,
             long long P, long long N, int C, const MmaKind* __restrict__ kinds, int nslices,
@@ -274,6 +338,19 @@ k_schur_mma(const double* __restrict__ tab, const double* __restrict__ pts,
       if (c >= nchunks) continue;
       double* s_Y = s_dyn + st * stage_doubles;
       const long long q0 = pa + c * SP;
+      if (PRE) {
+        // contiguous rows of Yg -> ring stage (16-byte chunks); the tail of the last chunk is zeroed
+        const int npc = (int)min((long long)SP, pb - q0);
+        const int nch = 3 * npc * rp / 2, nall = 3 * SP * rp / 2;
+        const double2* src = reinterpret_cast<const double2*>(Yg + (size_t)q0 * 3 * rp);
+        double2* dst2 = reinterpret_cast<double2*>(s_Y);
+        for (int i = ptid; i < nch; i += nprod) cp_async16(dst2 + i, src + i);
+        for (int i = nch + ptid; i < nall; i += nprod) dst2[i] = make_double2(0.0, 0.0);
+        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+        __threadfence_block();
+        nbar_arrive(BAR_FULL + st, nthreads);
+        continue;
+      }
       for (int idx = ptid; idx < total + SP; idx += nprod) {
         if (idx >= total) {   // the z row of point q (and the zero row behind it)
           const int q = idx - total;
