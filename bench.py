@@ -277,15 +277,18 @@ def main():
         mma = "cam_normal" in prof
         ms_schur = prof["schur"]["total_ms"] / prof["schur"]["launches"]
         ms_u = prof["cam_normal"]["total_ms"] / prof["cam_normal"]["launches"] if mma else 0.0
+        ms_y = prof["make_Y"]["total_ms"] / prof["make_Y"]["launches"] if "make_Y" in prof else 0.0
+        ms_u += ms_y          # helper passes of the tensor path: Y to HBM + camera blocks
         fl = schur_flops(k_loc, n_loc)
         kern_total = sum(v["total_ms"] for v in prof.values())
-        roof = {"kernel": "k_schur_mma (+ k_cam_normal)" if mma else "k_schur", "bound": "fp64",
+        roof = {"kernel": "k_schur_mma (+ k_make_Y + k_cam_normal)" if mma else "k_schur", "bound": "fp64",
                 "achieved": fl / (ms_schur + ms_u) * 1e-9,
                 "peak": fp64_peak, "unit": "TFLOP/s", "frac": fl / (ms_schur + ms_u) * 1e-9 / fp64_peak,
                 "traffic": None, "flop_per_launch": fl, "ms_per_launch": ms_schur + ms_u,
-                "ms_k_schur": ms_schur, "ms_k_cam_normal": ms_u,
-                "share_of_step": (prof["schur"]["total_ms"] + (prof["cam_normal"]["total_ms"] if mma else 0.0))
-                / kern_total,
+                "ms_k_schur": ms_schur, "ms_helpers": ms_u, "ms_k_make_Y": ms_y,
+                "frac_k_schur_alone": fl / ms_schur * 1e-9 / fp64_peak,
+                "share_of_step": (prof["schur"]["total_ms"] + (prof["cam_normal"]["total_ms"] if mma else 0.0)
+                                  + (prof["make_Y"]["total_ms"] if "make_Y" in prof else 0.0)) / kern_total,
                 "peak_source": "DFMA/DMMA microbenchmarks on this pool (profiles/r01_fp64_peak.txt)"}
     jac_bytes = 264.0 * n_loc + 24.0 * p_loc
     roof_m1 = {"kernel": "k_jacobian_blocks", "bound": "hbm", "achieved": jac_bytes / ms_jac * 1e-6,
@@ -299,7 +302,8 @@ def main():
         if ws == 1 and tr.get("n_obs") == N:
             t = tr["dram_bytes_per_launch"]
             if roof is not None:
-                roof["traffic"] = (t.get("k_schur_mma", 0) + t.get("k_cam_normal", 0)) or t.get("void k_schur<0>")
+                roof["traffic"] = ((t.get("k_schur_mma", 0) + t.get("k_cam_normal", 0) + t.get("k_make_Y", 0))
+                                   or t.get("void k_schur<0>"))
             roof_m1["traffic"] = t.get("k_jacobian_blocks")
     except Exception:
         pass

@@ -694,7 +694,7 @@ static int pass_linearize(lcba_t* h, int first) {
   KL(h, "linearize", k_linearize<<<h->lin_grid, LIN_THREADS, smem, h->stream>>>(
         h->d_tab[w], h->d_pts[w], h->d_uv, h->d_cam, h->d_pt, h->d_w, h->d_obs_start, h->d_bins,
         h->nbins, C, h->d_Vg, h->d_campart, h->d_part));
-  KL(h, "reduce", k_reduce_cols<<<nblk(C * CAMSUM, 128), 128, 0, h->stream>>>(
+  KL(h, "reduce", k_reduce_cols<<<nblk(C * CAMSUM, RC_COLS), RC_COLS * RC_ROWS, 0, h->stream>>>(
         h->d_campart, h->lin_grid, C * CAMSUM, h->d_camsum));
   KL(h, "reduce", k_reduce_scalars<<<1, 256, 0, h->stream>>>(h->d_part, h->lin_grid, 1,
                                                              h->d_camsum + C * CAMSUM, 1));
@@ -744,7 +744,7 @@ static int pass_schur(lcba_t* h, const double* lam_host_or_null) {
     const size_t smem_u = ((size_t)((C * CAMTAB + 1) & ~1) + (size_t)h->camn_pb * C) * 8;
     KL(h, "cam_normal", k_cam_normal<<<h->camn_grid, 256, smem_u, h->stream>>>(
           h->d_tab[w], h->d_pts[w], h->d_w, h->d_obs_start, h->d_mask, h->P, C, h->camn_pb, h->d_Upart));
-    KL(h, "reduce", k_reduce_cols<<<nblk(C * CAMN_VALS, 128), 128, 0, h->stream>>>(
+    KL(h, "reduce", k_reduce_cols<<<nblk(C * CAMN_VALS, RC_COLS), RC_COLS * RC_ROWS, 0, h->stream>>>(
           h->d_Upart, h->camn_grid, C * CAMN_VALS, h->d_U));
     const int nt = (NCP * C + 1 + 7) / 8, last = nt - 6 * ((nt + 5) / 6 - 1);
     if (h->d_Yg) {
@@ -775,7 +775,7 @@ static int pass_schur(lcba_t* h, const double* lam_host_or_null) {
       default: LCBA_MMA_LAUNCH(6); break;
     }
 #undef LCBA_MMA_LAUNCH
-    KL(h, "schur_reduce", k_reduce_cols<<<nblk((long long)pl.part_stride, 256), 256, 0, h->stream>>>(
+    KL(h, "schur_reduce", k_reduce_cols<<<nblk((long long)pl.part_stride, RC_COLS), RC_COLS * RC_ROWS, 0, h->stream>>>(
           h->d_Spart, mp.nslices, (int)pl.part_stride, h->d_Sred));
     KL(h, "schur_reduce", k_add_cam_blocks<<<nblk(C * 121, 128), 128, 0, h->stream>>>(h->d_U, C, h->d_Sred));
   } else {
@@ -789,7 +789,7 @@ static int pass_schur(lcba_t* h, const double* lam_host_or_null) {
   if (pl.cfg != 1) { if (skip) LCBA_SCHUR_LAUNCH(true, 160); else LCBA_SCHUR_LAUNCH(false, 160); }
   else             { if (skip) LCBA_SCHUR_LAUNCH(true, 128); else LCBA_SCHUR_LAUNCH(false, 128); }
 #undef LCBA_SCHUR_LAUNCH
-  KL(h, "schur_reduce", k_reduce_cols<<<nblk((long long)pl.part_stride, 256), 256, 0, h->stream>>>(
+  KL(h, "schur_reduce", k_reduce_cols<<<nblk((long long)pl.part_stride, RC_COLS), RC_COLS * RC_ROWS, 0, h->stream>>>(
         h->d_Spart, pl.nslices, (int)pl.part_stride, h->d_Sred));
   }
   LCBA_TRY(allreduce(h, h->d_Sred, pl.part_stride, NCCL_SUM));
@@ -1323,7 +1323,7 @@ extern "C" int lcba_sq_normal(lcba_t* h, int32_t mode, const double* theta, doub
       KL(h, "sq_transform_cost", k_sq_transform<false><<<grid, threads, smem, h->stream>>>(
             h->d_tab[cur], h->d_pts[cur], h->d_uv, h->d_cam, h->d_pt, h->d_w, h->N, C, h->d_theta, h->d_sqpart));
   }
-  KL(h, "reduce", k_reduce_cols<<<nblk(K, 128), 128, 0, h->stream>>>(h->d_sqpart, grid, K, h->d_sqout));
+  KL(h, "reduce", k_reduce_cols<<<nblk(K, RC_COLS), RC_COLS * RC_ROWS, 0, h->stream>>>(h->d_sqpart, grid, K, h->d_sqout));
   std::vector<double> v((size_t)K);
   LCBA_CUDA(h, cudaMemcpyAsync(v.data(), h->d_sqout, (size_t)K * 8, cudaMemcpyDeviceToHost, h->stream));
   LCBA_CUDA(h, cudaStreamSynchronize(h->stream));

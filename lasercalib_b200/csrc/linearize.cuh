@@ -167,14 +167,25 @@ k_linearize(const double* __restrict__ tab, const double* __restrict__ pts,
   if (t == 0) cost_part[blockIdx.x] = cs;
 }
 
-// out[j] = sum_b part[b*K + j]; one block per column group, fixed order.
-__global__ void k_reduce_cols(const double* __restrict__ part, int nblocks, int K,
-                              double* __restrict__ out) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= K) return;
-  double s = 0.0;
-  for (int b = 0; b < nblocks; ++b) s += part[(size_t)b * K + j];
-  out[j] = s;
+// out[j] = sum_b part[b*K + j], fixed order.  Block = 32 columns x 8 row lanes: lane r adds rows
+// r, r + 8, ... (coalesced 256-byte reads per row), the 8 partial sums are combined in order.
+constexpr int RC_COLS = 32, RC_ROWS = 8;
+__global__ void __launch_bounds__(RC_COLS * RC_ROWS)
+k_reduce_cols(const double* __restrict__ part, int nblocks, int K, double* __restrict__ out) {
+  __shared__ double s[RC_ROWS][RC_COLS + 1];
+  const int c = threadIdx.x % RC_COLS, r = threadIdx.x / RC_COLS;
+  const int j = blockIdx.x * RC_COLS + c;
+  double v = 0.0;
+  if (j < K)
+    for (int b = r; b < nblocks; b += RC_ROWS) v += part[(size_t)b * K + j];
+  s[r][c] = v;
+  __syncthreads();
+  if (r == 0 && j < K) {
+    double t = 0.0;
+#pragma unroll
+    for (int q = 0; q < RC_ROWS; ++q) t += s[q][c];
+    out[j] = t;
+  }
 }
 
 // few columns, many rows: one CTA per column
