@@ -174,6 +174,56 @@ def test_reduced_camera_system_vs_oracle(Engine, rig, npts, pvis, lam):
     eng.close()
 
 
+def _first_cameras(pb, C, min_views=3):
+    """The problem restricted to its first C cameras (points with too few views left dropped)."""
+    keep = pb["camera_ind"] < C
+    ci, pi, uv = pb["camera_ind"][keep], pb["point_ind"][keep], pb["points_2d"][keep]
+    cnt = np.bincount(pi, minlength=pb["pts0"].shape[0])
+    good = cnt >= min_views
+    sel = good[pi]
+    remap = np.cumsum(good) - 1
+    return dict(cams0=pb["cams0"][:C].copy(), pts0=pb["pts0"][good].copy(), points_2d=uv[sel].copy(),
+                camera_ind=ci[sel].copy(), point_ind=remap[pi[sel]].copy())
+
+
+@pytest.mark.parametrize("C", [8, 10, 12, 13, 15, 18, 22, 24, 32])
+def test_tensor_path_schur_equals_dfma_path(Engine, monkeypatch, C):
+    """The two Schur kernels (DMMA tiles, schur_mma.cuh; DFMA duo blocks, schur.cuh) against each
+    other and the oracle for every shape of the last tile group (11 C + 1 rows mod 48), with
+    weights, with Y precomputed in HBM (k_make_Y) and evaluated by the producers in place."""
+    base = make_rig("ring64" if C > 24 else "ring24", 260, seed=5, variant="volume", p_vis=0.93)
+    pb = _first_cameras(base, C)
+    ci, pi = pb["camera_ind"], pb["point_ind"]
+    w = np.random.default_rng(C).uniform(0.5, 2.0, ci.size)
+    outs = {}
+    for name, env in (("dfma", {"LCBA_SCHUR_MMA": "0"}), ("mma_pre", {"LCBA_SCHUR_MMA": "1", "LCBA_MMA_PRE": "1"}),
+                      ("mma_inplace", {"LCBA_SCHUR_MMA": "1", "LCBA_MMA_PRE": "0"})):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        eng = Engine()
+        eng.set_problem(pb["cams0"], pb["pts0"], pb["points_2d"], ci, pi, w)
+        outs[name] = eng.linearize(1e-3)
+        eng.close()
+        for k in env:
+            monkeypatch.delenv(k)
+    ref = outs["dfma"]
+    for name in ("mma_pre", "mma_inplace"):
+        o = outs[name]
+        assert np.abs(o["S"] - o["S"].T).max() == 0.0
+        assert np.abs(o["S"] - ref["S"]).max() <= 1e-12 * np.abs(ref["S"]).max()
+        assert np.abs(o["rhs"] - ref["rhs"]).max() <= 1e-11 * np.abs(ref["rhs"]).max()
+    np.testing.assert_array_equal(outs["mma_pre"]["S"], outs["mma_inplace"]["S"])     # same arithmetic
+    P = pb["pts0"].shape[0]
+    x0 = np.hstack((pb["cams0"].ravel(), pb["pts0"].ravel()))
+    f = O.fun(x0, C, P, ci, pi, pb["points_2d"], w.reshape(-1, 1))
+    _, Jc, Jp = O.jacobian_blocks(pb["cams0"], pb["pts0"], ci, pi, w)
+    U, gc, V, gp, W = O.normal_blocks(f.reshape(-1, 2), Jc, Jp, C, P, ci, pi)
+    sc = np.hstack((np.sqrt(np.einsum("caa->ca", U)).ravel(), np.sqrt(np.einsum("paa->pa", V)).ravel()))
+    S_or, rhs_or, _ = O.reduced_camera_system(U, gc, V, gp, W, ci, pi, 1e-3, sc)
+    assert np.abs(outs["mma_pre"]["S"] - S_or).max() <= 1e-11 * np.abs(S_or).max()
+    assert np.abs(outs["mma_pre"]["rhs"] - rhs_or).max() <= 1e-10 * np.abs(rhs_or).max()
+
+
 # ------------------------------------------------------------------------- P3 / P4 solver
 def _run_engine(Engine, g, **kw):
     eng = Engine()
