@@ -281,7 +281,10 @@ def main():
         ms_u += ms_y          # helper passes of the tensor path: Y to HBM + camera blocks
         fl = schur_flops(k_loc, n_loc)
         kern_total = sum(v["total_ms"] for v in prof.values())
-        roof = {"kernel": "k_schur_mma (+ k_make_Y + k_cam_normal)" if mma else "k_schur", "bound": "fp64",
+        # bound: the dense path runs on the tensor pipe (FP64 DMMA); its peak is the FP64 DMMA rate
+        # measured on this pool (MEASURED_PEAKS.json only has the bf16 tensor rate), see peak_source
+        roof = {"kernel": "k_schur_mma (+ k_make_Y + k_cam_normal)" if mma else "k_schur",
+                "bound": "tensor" if mma else "fp64", "precision": "fp64",
                 "achieved": fl / (ms_schur + ms_u) * 1e-9,
                 "peak": fp64_peak, "unit": "TFLOP/s", "frac": fl / (ms_schur + ms_u) * 1e-9 / fp64_peak,
                 "traffic": None, "flop_per_launch": fl, "ms_per_launch": ms_schur + ms_u,
@@ -289,7 +292,8 @@ def main():
                 "frac_k_schur_alone": fl / ms_schur * 1e-9 / fp64_peak,
                 "share_of_step": (prof["schur"]["total_ms"] + (prof["cam_normal"]["total_ms"] if mma else 0.0)
                                   + (prof["make_Y"]["total_ms"] if "make_Y" in prof else 0.0)) / kern_total,
-                "peak_source": "DFMA/DMMA microbenchmarks on this pool (profiles/r01_fp64_peak.txt)"}
+                "peak_source": "FP64 DMMA (mma.sync m8n8k4) / DFMA microbenchmarks on this pool "
+                               "(tools/fp64_peak.cu, profiles/r01_fp64_peak.txt): 37.1 TFLOP/s"}
     jac_bytes = 264.0 * n_loc + 24.0 * p_loc
     roof_m1 = {"kernel": "k_jacobian_blocks", "bound": "hbm", "achieved": jac_bytes / ms_jac * 1e-6,
                "peak": hbm_peak, "unit": "GB/s", "frac": jac_bytes / ms_jac * 1e-6 / hbm_peak,

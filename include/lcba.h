@@ -222,6 +222,11 @@ int lcba_comm_init(lcba_t* h, int32_t rank, int32_t nranks, const void* id128);
 int lcba_debug_tr2d(double B00, double B01, double B11, double g0, double g1, double Delta,
                     double* p_out2, int* newton_out);
 
+/* ---- profiling hook --------------------------------------------------------------------
+ * Per-CTA cycle counters of the last Schur launch (4 int64 per CTA, [kind][slice]); only
+ * filled when the process runs with LCBA_SCHUR_STATS=1 (tools/schur_stats.py). */
+int lcba_debug_schur_stats(lcba_t* h, long long* out, int max_ctas, int* nkinds, int* nslices);
+
 #ifdef __cplusplus
 }
 #endif

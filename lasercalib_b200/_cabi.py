@@ -20,7 +20,7 @@ SYMBOLS = ["lcba_version", "lcba_create", "lcba_destroy", "lcba_last_error", "lc
            "lcba_unproject", "lcba_residuals", "lcba_jacobian_blocks", "lcba_sparsity_indices", "lcba_solve",
            "lcba_get_trace", "lcba_get_grad", "lcba_get_profile", "lcba_linearize",
            "lcba_time_device", "lcba_nccl_unique_id", "lcba_comm_init", "lcba_debug_tr2d",
-           "lcba_sq_normal"]
+           "lcba_sq_normal", "lcba_debug_schur_stats"]
 
 
 class Options(C.Structure):
@@ -94,6 +94,7 @@ def load():
     lib.lcba_nccl_unique_id.argtypes = [vp]
     lib.lcba_comm_init.argtypes = [vp, i32, i32, vp]
     lib.lcba_sq_normal.argtypes = [vp, i32, vp, pd, vp, vp]
+    lib.lcba_debug_schur_stats.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.lcba_debug_tr2d.argtypes = [dbl, dbl, dbl, dbl, dbl, dbl, pd, C.POINTER(C.c_int)]
     _lib = lib
     return lib
@@ -163,9 +164,15 @@ class Engine:
         cams, pts = _f64(cams, (self.C, 11)), _f64(pts, (self.P, 3))
         self._check(self.lib.lcba_set_params(self.h, _ptr(cams), _ptr(pts)))
 
-    def get_params(self):
-        cams = np.empty((self.C, 11))
-        pts = np.empty((self.P, 3))
+    def get_params(self, x_out=None):
+        """(cams, pts) of the current iterate; with `x_out` (11 C + 3 P doubles, contiguous) the
+        two arrays are views into it, i.e. x_out becomes the reference's parameter vector."""
+        if x_out is None:
+            cams = np.empty((self.C, 11))
+            pts = np.empty((self.P, 3))
+        else:
+            cams = x_out[: 11 * self.C].reshape(self.C, 11)
+            pts = x_out[11 * self.C:].reshape(self.P, 3)
         self._check(self.lib.lcba_get_params(self.h, _ptr(cams), _ptr(pts)))
         return cams, pts
 

@@ -272,7 +272,11 @@ class PySBA:
             _print_header()
             for row in trace:
                 _print_row(row)
-        cams, pts = eng.get_params()
+        x_direct = None
+        if shard is None and not _fix_cameras and not _shared:
+            # the reference's x = [cameras | points]: filled in place, the arrays are views
+            x_direct = np.empty(numCameras * N_CAM_PARAMS + numPoints * 3)
+        cams, pts = eng.get_params(x_direct)
         if shard is not None:
             pts = _dist.allgather_rows(pts, shard["bounds"])
         if _fix_cameras:
@@ -293,10 +297,10 @@ class PySBA:
             self.cameraArray = cams
             self.points3D = pts
             return out
-        x = np.hstack((cams.ravel(), pts.ravel()))
+        x = x_direct if x_direct is not None else np.hstack((cams.ravel(), pts.ravel()))
         out = BAResult(x=x, cost=res.cost, optimality=res.optimality,
-                       active_mask=np.zeros_like(x), nfev=int(res.nfev), njev=int(res.njev),
-                       status=int(res.status))
+                       nfev=int(res.nfev), njev=int(res.njev), status=int(res.status))
+        out.set_lazy("active_mask", lambda: np.zeros_like(x))
         out["message"] = TERMINATION_MESSAGES[int(res.status)]
         out["success"] = int(res.status) > 0
         out["solve_ms"] = res.solve_ms
