@@ -227,6 +227,12 @@ int lcba_debug_tr2d(double B00, double B01, double B11, double g0, double g1, do
  * filled when the process runs with LCBA_SCHUR_STATS=1 (tools/schur_stats.py). */
 int lcba_debug_schur_stats(lcba_t* h, long long* out, int max_ctas, int* nkinds, int* nslices);
 
+/* Host-only: the unit plan of the tensor-path Schur kernel (schur_mma.cuh) for C cameras; per
+ * kind 8 rows of (first tile row, first tile column, tile rows, tile columns, triangular), a
+ * row of zeros = idle warp.  Returns the number of kinds (needs no GPU). */
+int lcba_debug_mma_plan(int32_t C, int32_t sm_count, int32_t* units_out, int32_t max_kinds,
+                        int32_t* nslices_out, int32_t* ok_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1277,6 +1277,23 @@ extern "C" int lcba_debug_schur_stats(lcba_t* h, long long* out, int max_ctas, i
   return LCBA_OK;
 }
 
+// host-only test hook: the unit plan of the tensor-path Schur kernel for C cameras (no GPU needed).
+// units_out: per kind MMA_CONS_WARPS rows of (tr0, tc0, nr, nc, tri); returns the number of kinds.
+extern "C" int lcba_debug_mma_plan(int32_t C, int32_t sm_count, int32_t* units_out, int32_t max_kinds,
+                                   int32_t* nslices_out, int32_t* ok_out) {
+  if (C < 1 || C > LCBA_MAX_CAMERAS || !units_out) return LCBA_E_ARG;
+  const MmaPlan pl = make_mma_plan(C, sm_count, 227 * 1024 - 2048);
+  if (ok_out) *ok_out = (pl.nkinds > 0 && C <= MMA_MAX_CAMERAS) ? 1 : 0;
+  if (nslices_out) *nslices_out = pl.nslices;
+  for (int k = 0; k < pl.nkinds && k < max_kinds; ++k)
+    for (int w = 0; w < MMA_CONS_WARPS; ++w) {
+      const MmaUnit& u = pl.kinds[k].unit[w];
+      int32_t* o = units_out + ((size_t)k * MMA_CONS_WARPS + w) * 5;
+      o[0] = u.tr0; o[1] = u.tc0; o[2] = u.nr; o[3] = u.nc; o[4] = u.tri;
+    }
+  return pl.nkinds;
+}
+
 // ---- squared-residual variants (pySBA.py:151-206): cost, J^T f, J^T J in one pass ----------
 extern "C" int lcba_sq_normal(lcba_t* h, int32_t mode, const double* theta, double* cost_out,
                               double* g_out, double* H_out) {

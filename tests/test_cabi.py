@@ -99,3 +99,36 @@ def test_tr2d_solver_matches_scipy(lib):
         assert val(p) <= val(ps) + 1e-6 * abs(val(ps)) + 1e-300
         if newton == newton_s and np.linalg.cond(B) < 1e8:
             np.testing.assert_allclose(p, ps, rtol=1e-7, atol=1e-9 * D)
+
+
+def test_tensor_path_unit_plan_covers_every_tile_once():
+    """Host logic of the tensor-path Schur kernel (schur_mma.cuh make_mma_plan, no GPU): for every
+    camera count the units tile the lower triangle of the (11 C + 1)-row matrix exactly once,
+    every kind fits 8 consumer warps, and the busiest SM sub-partition (warp w -> w % 4) stays
+    within 40 % of the mean load (10 % at the 24 cameras of the benchmark)."""
+    import ctypes as C
+    from lasercalib_b200 import _cabi
+    lib = _cabi.load()
+    for cams in range(8, 33):
+        buf = np.zeros((16, 8, 5), dtype=np.int32)
+        ns, ok = C.c_int32(), C.c_int32()
+        nk = lib.lcba_debug_mma_plan(cams, 148, buf.ctypes.data_as(C.c_void_p), 16, C.byref(ns), C.byref(ok))
+        assert nk >= 1 and ok.value == 1 and ns.value == 148 // nk
+        nt = (11 * cams + 1 + 7) // 8
+        cover = np.zeros((nt, nt), dtype=int)
+        worst = 0.0
+        for k in range(nk):
+            load = np.zeros(4)
+            for w in range(8):
+                tr0, tc0, nr, nc, tri = buf[k, w]
+                for t in range(nr):
+                    for u in range(nc):
+                        if tri and u > t:
+                            continue
+                        cover[tr0 + t, tc0 + u] += 1
+                        load[w % 4] += 1
+            assert load.sum() > 0
+            worst = max(worst, load.max() / load.mean())
+        low = np.tril(np.ones((nt, nt), dtype=int))
+        np.testing.assert_array_equal(cover, low)
+        assert worst <= (1.10 if cams == 24 else 1.40), (cams, worst)
