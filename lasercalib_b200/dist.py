@@ -130,24 +130,40 @@ def connect_engine(engine):
     _process_comm[ws] = True
 
 
-def allgather_rows(local, bounds):
-    """Concatenate per-rank row blocks (rank r holds rows bounds[r]:bounds[r+1]) on every rank."""
+def allgather_rows(local, bounds, out=None):
+    """Concatenate per-rank row blocks (rank r holds rows bounds[r]:bounds[r+1]) on every rank.
+    `out` (total rows x width, float64) is filled in place when given.  One collective into a
+    single buffer and one device-to-host copy."""
     import torch
     import torch.distributed as dist
     rank, ws, _ = world()
     if ws == 1:
+        if out is not None:
+            out[...] = local
+            return out
         return local
-    local = np.ascontiguousarray(local)
+    local = np.ascontiguousarray(local, dtype=np.float64)
     width = local.shape[1]
     dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" \
         else torch.device("cpu")
     sizes = [int(bounds[r + 1] - bounds[r]) for r in range(ws)]
     mx = max(max(sizes), 1)
     buf = torch.zeros((mx, width), dtype=torch.float64, device=dev)
-    buf[: local.shape[0]] = torch.from_numpy(local).to(dev)
-    outs = [torch.empty_like(buf) for _ in range(ws)]
-    dist.all_gather(outs, buf)
-    return np.concatenate([o[: sizes[r]].cpu().numpy() for r, o in enumerate(outs)], axis=0)
+    buf[: local.shape[0]].copy_(torch.from_numpy(local))
+    big = torch.empty((ws * mx, width), dtype=torch.float64, device=dev)
+    try:
+        dist.all_gather_into_tensor(big, buf)
+    except (RuntimeError, AttributeError, NotImplementedError):
+        outs = [torch.empty_like(buf) for _ in range(ws)]
+        dist.all_gather(outs, buf)
+        big = torch.cat(outs, dim=0)
+    host = big.cpu().numpy().reshape(ws, mx, width)
+    if out is None:
+        out = np.empty((int(bounds[ws] - bounds[0]), width))
+    for r in range(ws):
+        a = int(bounds[r] - bounds[0])
+        out[a:a + sizes[r]] = host[r, : sizes[r]]
+    return out
 
 
 def allreduce_sum(arr):

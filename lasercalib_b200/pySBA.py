@@ -273,12 +273,20 @@ class PySBA:
             for row in trace:
                 _print_row(row)
         x_direct = None
-        if shard is None and not _fix_cameras and not _shared:
+        nc = numCameras * N_CAM_PARAMS
+        if not _fix_cameras and not _shared:
             # the reference's x = [cameras | points]: filled in place, the arrays are views
-            x_direct = np.empty(numCameras * N_CAM_PARAMS + numPoints * 3)
-        cams, pts = eng.get_params(x_direct)
-        if shard is not None:
-            pts = _dist.allgather_rows(pts, shard["bounds"])
+            x_direct = np.empty(nc + numPoints * 3)
+        if shard is None:
+            cams, pts = eng.get_params(x_direct)
+        else:
+            cams, pts = eng.get_params()
+            if x_direct is not None:
+                x_direct[:nc] = cams.ravel()
+                cams = x_direct[:nc].reshape(numCameras, N_CAM_PARAMS)
+                pts = _dist.allgather_rows(pts, shard["bounds"], out=x_direct[nc:].reshape(numPoints, 3))
+            else:
+                pts = _dist.allgather_rows(pts, shard["bounds"])
         if _fix_cameras:
             return self._finish_nocam(eng, res, pts, shard, verbose)
         if _shared:
