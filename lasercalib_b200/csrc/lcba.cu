@@ -459,7 +459,19 @@ extern "C" int lcba_set_problem_shard(lcba_t* h, int32_t C, int64_t P, int64_t N
     const char* env = getenv("LCBA_SCHUR_MMA");
     const bool want = env ? atoi(env) != 0 : (dense && C >= 8);
     if (want && C <= MMA_MAX_CAMERAS) {
-      h->mplan = make_mma_plan(C, h->sm_count, h->smem_optin - 2048);
+      // Y precomputed in HBM when it fits comfortably (288 B per (point, camera)); otherwise the
+      // producers of k_schur_mma evaluate it in place (and need the camera tables in shared memory)
+      bool pre = false;
+      {
+        int rp = C * 12 + 2;
+        while (rp % 16 != 4) ++rp;
+        const size_t need = (size_t)(P + 1) * 3 * rp * 8;
+        size_t fr = 0, tot = 0;
+        const char* pe = getenv("LCBA_MMA_PRE");
+        pre = cudaMemGetInfo(&fr, &tot) == cudaSuccess && need < fr / 3 && !(pe && atoi(pe) == 0);
+        if (pre) LCBA_TRY(dev_alloc(h, &h->d_Yg, need / 8));
+      }
+      h->mplan = make_mma_plan(C, h->sm_count, h->smem_optin - 2048, !pre);
       LCBA_TRY(dev_alloc(h, &h->d_mkinds, h->mplan.kinds.size()));
       LCBA_CUDA(h, cudaMemcpyAsync(h->d_mkinds, h->mplan.kinds.data(), h->mplan.kinds.size() * sizeof(MmaKind),
                                    cudaMemcpyHostToDevice, st));
@@ -470,15 +482,6 @@ extern "C" int lcba_set_problem_shard(lcba_t* h, int32_t C, int64_t P, int64_t N
       LCBA_TRY(dev_alloc(h, &h->d_U, (size_t)C * CAMN_VALS));
       max_slices = std::max(max_slices, h->mplan.nslices);
       h->use_mma = true;
-      // Y precomputed in HBM when it fits comfortably (288 B per (point, camera)); otherwise the
-      // producers of k_schur_mma evaluate it in place
-      {
-        const size_t need = (size_t)(P + 1) * 3 * h->mplan.kinds[0].rp * 8;
-        size_t fr = 0, tot = 0;
-        const char* pe = getenv("LCBA_MMA_PRE");
-        if (cudaMemGetInfo(&fr, &tot) == cudaSuccess && need < fr / 3 && !(pe && atoi(pe) == 0))
-          LCBA_TRY(dev_alloc(h, &h->d_Yg, need / 8));
-      }
     }
   }
   LCBA_TRY(dev_alloc(h, &h->d_Spart, h->plan.part_stride * max_slices));

@@ -57,7 +57,9 @@ struct MmaPlan {
   std::vector<MmaKind> kinds;
 };
 
-inline MmaPlan make_mma_plan(int C, int sm_count, size_t smem_limit) {
+// need_tab: the producers evaluate Y in place and keep the camera tables in shared memory; with
+// Y precomputed (k_make_Y) that space goes to the ring (24 cameras: 16 instead of 12 points per stage)
+inline MmaPlan make_mma_plan(int C, int sm_count, size_t smem_limit, bool need_tab = true) {
   MmaPlan pl;
   pl.C = C;
   const int nrows = NCP * C + 1, nt = (nrows + 7) / 8, ng = (nt + 5) / 6;
@@ -101,7 +103,7 @@ inline MmaPlan make_mma_plan(int C, int sm_count, size_t smem_limit) {
   }
   int rp = C * 12 + 2;
   while (rp % 16 != 4) ++rp;
-  const size_t fixed = (size_t)C * CAMTAB * 8 + 64;
+  const size_t fixed = (need_tab ? (size_t)C * CAMTAB * 8 : 0) + 64;
   int sp = (int)((smem_limit - fixed) / ((size_t)3 * rp * 8 * SCHUR_STAGES));
   sp = std::max(4, std::min(16, sp / 4 * 4));
   pl.smem_bytes = (size_t)3 * sp * rp * 8 * SCHUR_STAGES + fixed;
@@ -332,8 +334,10 @@ k_schur_mma(const double* __restrict__ Yg, const double* __restrict__ tab, const
     // ================================ producer warpgroup ================================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 " MMA_PROD_REGS ";");
     const int ptid = tid - 32 * MMA_CONS_WARPS, nprod = 32 * MMA_PROD_WARPS;
-    for (int i = ptid; i < C * CAMTAB; i += nprod) s_tab[i] = tab[i];
-    nbar_sync(BAR_PROD, nprod);
+    if (!PRE) {
+      for (int i = ptid; i < C * CAMTAB; i += nprod) s_tab[i] = tab[i];
+      nbar_sync(BAR_PROD, nprod);
+    }
     const int total = SP * C;
     for (long long c = 0; c < nchunks + SCHUR_STAGES; ++c) {
       const int st = (int)(c % SCHUR_STAGES);
