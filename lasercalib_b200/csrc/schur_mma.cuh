@@ -183,8 +183,8 @@ __device__ __forceinline__ int mma_row_offset(int rho, int C) {
 // otherwise.
 // Block = 128 / C points at a time (small blocks: several per SM overlap their two phases):
 // thread (camera t % C, point t / C) evaluates its item into a
-// shared-memory tile that has the global layout, then the whole tile (contiguous in Yg) is
-// written with coalesced 16-byte stores.
+// shared-memory tile that has the global layout, then the whole tile (contiguous in Yg) goes
+// out as one TMA bulk store.
 constexpr int MAKEY_THREADS = 128;
 __global__ void __launch_bounds__(MAKEY_THREADS)
 k_make_Y(const double* __restrict__ tab, const double* __restrict__ pts,
@@ -222,13 +222,22 @@ k_make_Y(const double* __restrict__ tab, const double* __restrict__ pts,
         }
       }
     }
+    // the tile is one contiguous range of Yg: a single TMA bulk store (cp.async.bulk shared ->
+    // global) issued by one thread; the other blocks of the SM keep computing meanwhile
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
-    const int n2 = 3 * npts * rp / 2;
-    double2* dst = reinterpret_cast<double2*>(Yg + (size_t)p0 * 3 * rp);
-    const double2* src = reinterpret_cast<const double2*>(tile);
-    for (int i = t; i < n2; i += MAKEY_THREADS) dst[i] = src[i];
+    if (t == 0) {
+      const unsigned src = (unsigned)__cvta_generic_to_shared(tile);
+      const unsigned bytes = (unsigned)(3 * npts * rp * 8);
+      double* dst = Yg + (size_t)p0 * 3 * rp;
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes)
+                   : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // tile may be rewritten
+    }
     __syncthreads();
   }
+  if (t == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
