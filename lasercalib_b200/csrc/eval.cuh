@@ -84,11 +84,19 @@ k_residual(const double* __restrict__ tab, const double* __restrict__ pts,
 }
 
 // ---- residual + Jacobian blocks materialised to HBM (metric M1) --------------------
-// One thread per observation; each warp stages its 32 x (2x11 | 2x3) blocks in shared
-// memory and streams them out with coalesced 128-bit stores.  264 B/obs algorithmic.
+// One thread per observation; each warp stages its 32 x (2x11 | 2x3) blocks in shared memory in
+// the OUTPUT layout (conflict-free 128-bit stores: lane strides of 176 B and 48 B) and lane 0
+// sends them out as two TMA bulk stores (cp.async.bulk shared -> global: 5632 B + 1536 B,
+// contiguous in Jc / Jp).  264 B/obs algorithmic.  Unsorted input (perm) scatters per row instead.
 constexpr int JB_THREADS = 256;
 constexpr int JB_STAGE = 22 + 6;   // doubles per observation in the staging tile
-constexpr int JB_LD = 33;           // odd leading dimension: conflict-free transpose
+constexpr int JB_LD = 32;           // observations per warp tile
+
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, unsigned bytes) {
+  const unsigned src = (unsigned)__cvta_generic_to_shared(ssrc);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(src), "r"(bytes)
+               : "memory");
+}
 
 __global__ void __launch_bounds__(JB_THREADS)
 k_jacobian_blocks(const double* __restrict__ tab, const double* __restrict__ pts,
@@ -97,66 +105,67 @@ k_jacobian_blocks(const double* __restrict__ tab, const double* __restrict__ pts
                   const int32_t* __restrict__ perm, long long N, int C,
                   double2* __restrict__ r_out, double* __restrict__ Jc_out,
                   double* __restrict__ Jp_out) {
-  extern __shared__ double s_dyn[];
+  extern __shared__ __align__(16) double s_dyn[];
   double* s_tab = s_dyn;                                         // C*CAMTAB
   double* s_stage = s_dyn + ((C * CAMTAB + 1) & ~1);             // warps * JB_LD * JB_STAGE
   load_tables_smem(tab, s_tab, C);
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  double* st = s_stage + (size_t)wid * JB_LD * JB_STAGE;
+  double* sc = s_stage + (size_t)wid * JB_LD * JB_STAGE;         // [32][22]
+  double* sp = sc + JB_LD * 22;                                  // [32][6]
   const long long nwarps_total = (long long)gridDim.x * (JB_THREADS / 32);
   const long long ngroups = (N + 31) / 32;
   for (long long g = (long long)blockIdx.x * (JB_THREADS / 32) + wid; g < ngroups;
        g += nwarps_total) {
     const long long i = g * 32 + lane;
     const bool active = i < N;
-    double w = 1.0;
     if (active) {
       const int c = cam[i];
       const long long p = pt[i];
       const double2 o = uv[i];
-      w = wgt ? wgt[i] : 1.0;
+      const double w = wgt ? wgt[i] : 1.0;
       ObsLin L;
       obs_linearize<true>(s_tab + c * CAMTAB, pts[3 * p], pts[3 * p + 1], pts[3 * p + 2], o.x, o.y,
                           w, L);
       if (r_out) r_out[perm ? (long long)perm[i] : i] = make_double2(L.ru, L.rv);
-      // element-major staging: element a of this lane at st[a*JB_LD + lane]
-#pragma unroll
-      for (int a = 0; a < 9; ++a) {
-        st[a * JB_LD + lane] = L.Jc[0][a];
-        st[(11 + a) * JB_LD + lane] = L.Jc[1][a];
-      }
-      st[9 * JB_LD + lane] = w;
-      st[10 * JB_LD + lane] = 0.0;
-      st[20 * JB_LD + lane] = 0.0;
-      st[21 * JB_LD + lane] = w;
-#pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        st[(22 + a) * JB_LD + lane] = L.Jp[0][a];
-        st[(25 + a) * JB_LD + lane] = L.Jp[1][a];
-      }
+      double2* jc = reinterpret_cast<double2*>(sc + lane * 22);
+      jc[0] = make_double2(L.Jc[0][0], L.Jc[0][1]);
+      jc[1] = make_double2(L.Jc[0][2], L.Jc[0][3]);
+      jc[2] = make_double2(L.Jc[0][4], L.Jc[0][5]);
+      jc[3] = make_double2(L.Jc[0][6], L.Jc[0][7]);
+      jc[4] = make_double2(L.Jc[0][8], w);
+      jc[5] = make_double2(0.0, L.Jc[1][0]);
+      jc[6] = make_double2(L.Jc[1][1], L.Jc[1][2]);
+      jc[7] = make_double2(L.Jc[1][3], L.Jc[1][4]);
+      jc[8] = make_double2(L.Jc[1][5], L.Jc[1][6]);
+      jc[9] = make_double2(L.Jc[1][7], L.Jc[1][8]);
+      jc[10] = make_double2(0.0, w);
+      double2* jp = reinterpret_cast<double2*>(sp + lane * 6);
+      jp[0] = make_double2(L.Jp[0][0], L.Jp[0][1]);
+      jp[1] = make_double2(L.Jp[0][2], L.Jp[1][0]);
+      jp[2] = make_double2(L.Jp[1][1], L.Jp[1][2]);
     }
-    __syncwarp();
     const long long base = g * 32;
     const int nvalid = (int)min((long long)32, N - base);
     if (!perm) {
-      // contiguous output: Jc rows [base, base+nvalid) x 22, Jp x 6
-      double* jc = Jc_out + base * 22;
-      for (int e = lane; e < nvalid * 22; e += 32) jc[e] = st[(e % 22) * JB_LD + (e / 22)];
-      double* jp = Jp_out + base * 6;
-      for (int e = lane; e < nvalid * 6; e += 32) jp[e] = st[(22 + e % 6) * JB_LD + (e / 6)];
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        bulk_store(Jc_out + base * 22, sc, (unsigned)(nvalid * 22 * 8));
+        bulk_store(Jp_out + base * 6, sp, (unsigned)(nvalid * 6 * 8));
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // tile may be rewritten
+      }
     } else {
-      for (int e = lane; e < nvalid * 22; e += 32) {
-        const int ob = e / 22;
-        Jc_out[(long long)perm[base + ob] * 22 + (e % 22)] = st[(e % 22) * JB_LD + ob];
-      }
-      for (int e = lane; e < nvalid * 6; e += 32) {
-        const int ob = e / 6;
-        Jp_out[(long long)perm[base + ob] * 6 + (e % 6)] = st[(22 + e % 6) * JB_LD + ob];
-      }
+      __syncwarp();
+      for (int e = lane; e < nvalid * 22; e += 32)
+        Jc_out[(long long)perm[base + e / 22] * 22 + (e % 22)] = sc[e];
+      for (int e = lane; e < nvalid * 6; e += 32)
+        Jp_out[(long long)perm[base + e / 6] * 6 + (e % 6)] = sp[e];
     }
     __syncwarp();
   }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // ---- 3-D initialisation: Unproject (lasercalib/rigid_body.py:205-243) --------------------
