@@ -20,7 +20,8 @@ def main():
     rank, ws, local = D.init_from_env()
     assert ws > 1
     torch.cuda.set_device(local)
-    pb = make_rig("ring24", 20000, seed=3, variant="volume", p_vis=0.6)
+    # dense rig: the tensor-path Schur kernel (k_make_Y + k_schur_mma) together with NCCL
+    pb = make_rig("ring24", 20000, seed=3, variant="volume", p_vis=0.95)
     # single-GPU reference on every rank's own device
     eng = Engine(local)
     eng.set_problem(pb["cams0"], pb["pts0"], pb["points_2d"], pb["camera_ind"], pb["point_ind"])

@@ -224,6 +224,68 @@ def test_tensor_path_schur_equals_dfma_path(Engine, monkeypatch, C):
     assert np.abs(outs["mma_pre"]["rhs"] - rhs_or).max() <= 1e-10 * np.abs(rhs_or).max()
 
 
+def _oracle_reduced(pb, lam, w=None):
+    C, P = pb["n_cams"], pb["n_points"]
+    ci, pi = pb["camera_ind"], pb["point_ind"]
+    wcol = O.default_weights(pi) if w is None else w.reshape(-1, 1)
+    x0 = np.hstack((pb["cams0"].ravel(), pb["pts0"].ravel()))
+    f = O.fun(x0, C, P, ci, pi, pb["points_2d"], wcol)
+    _, Jc, Jp = O.jacobian_blocks(pb["cams0"], pb["pts0"], ci, pi, w)
+    U, gc, V, gp, W = O.normal_blocks(f.reshape(-1, 2), Jc, Jp, C, P, ci, pi)
+    sc = np.hstack((np.sqrt(np.einsum("caa->ca", U)).ravel(), np.sqrt(np.einsum("paa->pa", V)).ravel()))
+    S, rhs, _ = O.reduced_camera_system(U, gc, V, gp, W, ci, pi, lam, sc)
+    return S, rhs, 0.5 * f @ f
+
+
+@pytest.mark.parametrize("npts,weighted", [(20000, False), (20011, True)])
+def test_tensor_path_dense_many_ring_laps_vs_oracle(Engine, monkeypatch, npts, weighted):
+    """The headline configuration of the tensor-path Schur kernel at depth: ring24, full
+    visibility, ~400 points (25 chunks of 16) per point slice, so the 2-stage ring of
+    k_schur_mma wraps many times, k_make_Y loops over many tiles and every slice reduces many
+    chunk partials.  20011 points leave a ragged tail (not a multiple of 16 x nslices).
+    S / rhs against the numpy oracle (O.reduced_camera_system): 1e-11 / 1e-10 matrix-relative,
+    with Y from HBM (k_make_Y) and evaluated in place by the producers."""
+    pb = make_rig("ring24", npts, seed=7, variant="volume", p_vis=1.0)
+    assert pb["n_obs"] >= 0.99 * 24 * pb["n_points"]          # dense: the DMMA path by default
+    w = np.random.default_rng(3).uniform(0.5, 2.0, pb["n_obs"]) if weighted else None
+    S_or, rhs_or, cost_or = _oracle_reduced(pb, 1e-5, w)
+    outs = {}
+    for name, env in (("mma_pre", {"LCBA_MMA_PRE": "1"}), ("mma_inplace", {"LCBA_MMA_PRE": "0"}),
+                      ("dfma", {"LCBA_SCHUR_MMA": "0"})):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        eng = Engine()
+        eng.set_problem(pb["cams0"], pb["pts0"], pb["points_2d"], pb["camera_ind"], pb["point_ind"], w)
+        outs[name] = eng.linearize(1e-5)
+        eng.close()
+        for k in env:
+            monkeypatch.delenv(k)
+    for name, o in outs.items():
+        np.testing.assert_allclose(o["cost"], cost_or, rtol=1e-12, err_msg=name)
+        assert np.abs(o["S"] - o["S"].T).max() == 0.0, name
+        assert np.abs(o["S"] - S_or).max() <= 1e-11 * np.abs(S_or).max(), name
+        assert np.abs(o["rhs"] - rhs_or).max() <= 1e-10 * np.abs(rhs_or).max(), name
+    np.testing.assert_array_equal(outs["mma_pre"]["S"], outs["mma_inplace"]["S"])     # same arithmetic
+
+
+def test_dense_ring24_trajectory_matches_oracle(Engine):
+    """One full bundleAdjust(1e-4) trajectory on the dense 24-camera rig (5000 points: every
+    point slice several ring laps deep) against the same algorithm on the CPU."""
+    pb = make_rig("ring24", 5000, seed=11, variant="volume", p_vis=1.0)
+    ora = O.trf_exact(pb["cams0"], pb["pts0"], pb["points_2d"], pb["camera_ind"], pb["point_ind"],
+                      ftol=1e-4)
+    eng = Engine()
+    eng.set_problem(pb["cams0"], pb["pts0"], pb["points_2d"], pb["camera_ind"], pb["point_ind"])
+    res, trace = eng.solve(ftol=1e-4)
+    f, _ = eng.residuals()
+    eng.close()
+    assert res.nfev == ora.nfev and res.njev == ora.njev and res.status == ora.status
+    costs_o = [rec["cost"] for rec in ora.trace] + [ora.cost]
+    np.testing.assert_allclose([row["cost"] for row in trace], costs_o, rtol=3e-7)
+    np.testing.assert_allclose(res.cost, ora.cost, rtol=1e-8)
+    assert abs(O.rmse_px(f) - O.rmse_px(ora.fun)) < 1e-6      # north-star RMSE tolerance
+
+
 # ------------------------------------------------------------------------- P3 / P4 solver
 def _run_engine(Engine, g, **kw):
     eng = Engine()
