@@ -123,7 +123,10 @@ void lcba_default_options(lcba_options* o);
  * cams C x 11, pts P x 3, obs_uv N x 2 (row-major FP64); cam_idx / pt_idx N int64;
  * weights N FP64 or NULL (the reference's default is integer ones).  Observations in any
  * order; the library validates indices, sorts point-major / camera-ascending on the
- * device when needed and remembers the permutation. */
+ * device when needed and remembers the permutation.  A (camera, point) pair observed more
+ * than once is accepted like the reference accepts it (one more residual pair each; the
+ * reference's own dataset concatenation produces such rows for 3 or more laser datasets,
+ * calibrate_camera.py:41-44). */
 int lcba_set_problem(lcba_t* h, int32_t C, int64_t P, int64_t N, const double* cams,
                      const double* pts, const double* obs_uv, const int64_t* cam_idx,
                      const int64_t* pt_idx, const double* weights_or_null);
@@ -169,7 +172,9 @@ int lcba_sq_normal(lcba_t* h, int32_t mode, const double* theta, double* cost_ou
                    double* H_out);
 
 /* ---- PySBA.fun (pySBA.py:92-101) --------------------------------------------------
- * x_or_null: 11C + 3P parameters (NULL = the handle's current x). r_out: 2N or NULL. */
+ * x_or_null: 11C + 3P parameters (NULL = the handle's current x). r_out: 2N or NULL.
+ * cost_out != NULL: 0.5 |f|^2 over ALL ranks (collective on a point-sharded job: every rank
+ * must call); cost_out == NULL: this handle's residuals only, no collective. */
 int lcba_residuals(lcba_t* h, const double* x_or_null, double* r_out, double* cost_out);
 
 /* ---- the Jacobian scipy differentiates numerically (scipy/optimize/_numdiff.py:770) --
@@ -188,6 +193,11 @@ int lcba_sparsity_indices(lcba_t* h, int32_t C, int64_t P, int64_t N, const int6
  * equations in place of LSMR.  Updates the handle's x in place. */
 int lcba_solve(lcba_t* h, const lcba_options* opt, lcba_result* res);
 int lcba_get_trace(lcba_t* h, lcba_trace_row* rows, int32_t max_rows);
+/* Called by lcba_solve, on the calling thread, as soon as a row of scipy's verbose=2 table is
+ * known: scipy prints the table live (least_squares(verbose=2), pySBA.py:141;
+ * _lsq/common.py:551-563), so the host prints from here.  cb == NULL clears it. */
+typedef void (*lcba_iteration_cb)(const lcba_trace_row* row, void* user);
+int lcba_set_iteration_callback(lcba_t* h, lcba_iteration_cb cb, void* user);
 int lcba_get_grad(lcba_t* h, double* g_out /* 11C + 3P, at the current x */);
 int lcba_get_profile(lcba_t* h, lcba_kernel_stat* stats, int32_t max_stats, int32_t* n_out);
 

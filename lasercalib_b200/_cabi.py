@@ -20,7 +20,8 @@ SYMBOLS = ["lcba_version", "lcba_create", "lcba_destroy", "lcba_last_error", "lc
            "lcba_unproject", "lcba_residuals", "lcba_jacobian_blocks", "lcba_sparsity_indices", "lcba_solve",
            "lcba_get_trace", "lcba_get_grad", "lcba_get_profile", "lcba_linearize",
            "lcba_time_device", "lcba_nccl_unique_id", "lcba_comm_init", "lcba_debug_tr2d",
-           "lcba_sq_normal", "lcba_debug_schur_stats", "lcba_debug_mma_plan"]
+           "lcba_sq_normal", "lcba_debug_schur_stats", "lcba_debug_mma_plan",
+           "lcba_set_iteration_callback"]
 
 
 class Options(C.Structure):
@@ -44,6 +45,14 @@ class Result(C.Structure):
 
 class KernelStat(C.Structure):
     _fields_ = [("name", C.c_char * 32), ("launches", C.c_int64), ("total_ms", C.c_double)]
+
+
+ITERATION_CB = C.CFUNCTYPE(None, C.POINTER(TraceRow), C.c_void_p)
+
+
+def _row_dict(r):
+    return dict(iteration=r.iteration, nfev=r.nfev, cost=r.cost, cost_reduction=r.cost_reduction,
+                step_norm=r.step_norm, optimality=r.optimality, delta=r.delta, reg_term=r.reg_term)
 
 
 class LcbaError(RuntimeError):
@@ -87,6 +96,7 @@ def load():
     lib.lcba_sparsity_indices.argtypes = [vp, i32, i64, i64, vp, vp, vp]
     lib.lcba_solve.argtypes = [vp, C.POINTER(Options), C.POINTER(Result)]
     lib.lcba_get_trace.argtypes = [vp, C.POINTER(TraceRow), i32]
+    lib.lcba_set_iteration_callback.argtypes = [vp, ITERATION_CB, vp]
     lib.lcba_get_grad.argtypes = [vp, vp]
     lib.lcba_get_profile.argtypes = [vp, C.POINTER(KernelStat), i32, C.POINTER(i32)]
     lib.lcba_linearize.argtypes = [vp, dbl, vp, vp, vp, vp, pd]
@@ -127,6 +137,9 @@ class Engine:
             raise LcbaError(rc, self.lib.lcba_last_error(None).decode())
         self.h = h
         self.C = self.P = self.N = 0
+        # bumped by every call that changes what the handle holds (observation set or x): lazy
+        # readers (res.fun / res.grad / res.jac) compare it with the value they were created at
+        self.generation = 0
 
     def close(self):
         if getattr(self, "h", None):
@@ -160,8 +173,10 @@ class Engine:
                                                     _ptr(cams), _ptr(pts), _ptr(p2), _ptr(ci),
                                                     _ptr(pi), _ptr(w), int(pt_offset)))
         self.C, self.P, self.N = cams.shape[0], pts.shape[0], N
+        self.generation += 1
 
     def set_params(self, cams, pts):
+        self.generation += 1
         cams, pts = _f64(cams, (self.C, 11)), _f64(pts, (self.P, 3))
         self._check(self.lib.lcba_set_params(self.h, _ptr(cams), _ptr(pts)))
 
@@ -208,14 +223,17 @@ class Engine:
                                             _ptr(K), _ptr(d), _ptr(R), _ptr(t), _ptr(out)))
         return out
 
-    def residuals(self, x=None, want_r=True):
+    def residuals(self, x=None, want_r=True, want_cost=True):
+        """(r, cost).  want_cost=False: this handle's residuals only and NO collective, so one
+        rank of a point-sharded job may call it alone (cost is returned as None)."""
         x = None if x is None else _f64(x).ravel()
         if x is not None and x.size != 11 * self.C + 3 * self.P:
             raise ValueError("params has the wrong size")
         r = np.empty(2 * self.N) if want_r else None
         cost = C.c_double()
-        self._check(self.lib.lcba_residuals(self.h, _ptr(x), _ptr(r), C.byref(cost)))
-        return r, cost.value
+        self._check(self.lib.lcba_residuals(self.h, _ptr(x), _ptr(r),
+                                            C.byref(cost) if want_cost else None))
+        return r, (cost.value if want_cost else None)
 
     SQ_CAMONLY, SQ_TRANSFORM = 0, 1
 
@@ -250,7 +268,10 @@ class Engine:
 
     # ---- solver ----
     def solve(self, ftol=1e-8, xtol=1e-8, gtol=1e-8, max_nfev=0, verbose=0, profile=False,
-              max_iterations=0, fix_cameras=False, shared_intrinsics=False):
+              max_iterations=0, fix_cameras=False, shared_intrinsics=False, on_iteration=None):
+        """on_iteration(row_dict): called from inside lcba_solve as each row of scipy's
+        verbose=2 table becomes known (live printing)."""
+        self.generation += 1
         opt = Options()
         self.lib.lcba_default_options(C.byref(opt))
         opt.ftol, opt.xtol, opt.gtol = ftol, xtol, gtol
@@ -261,13 +282,18 @@ class Engine:
         opt.fix_cameras = 1 if fix_cameras else 0
         opt.shared_intrinsics = 1 if shared_intrinsics else 0
         res = Result()
-        self._check(self.lib.lcba_solve(self.h, C.byref(opt), C.byref(res)))
+        cb = None
+        if on_iteration is not None:
+            cb = ITERATION_CB(lambda row, _user: on_iteration(_row_dict(row.contents)))
+            self.lib.lcba_set_iteration_callback(self.h, cb, None)
+        try:
+            self._check(self.lib.lcba_solve(self.h, C.byref(opt), C.byref(res)))
+        finally:
+            if cb is not None:
+                self.lib.lcba_set_iteration_callback(self.h, ITERATION_CB(), None)
         rows = (TraceRow * LCBA_MAX_TRACE)()
         n = self.lib.lcba_get_trace(self.h, rows, LCBA_MAX_TRACE)
-        trace = [dict(iteration=r.iteration, nfev=r.nfev, cost=r.cost,
-                      cost_reduction=r.cost_reduction, step_norm=r.step_norm,
-                      optimality=r.optimality, delta=r.delta, reg_term=r.reg_term)
-                 for r in rows[:max(n, 0)]]
+        trace = [_row_dict(r) for r in rows[:max(n, 0)]]
         return res, trace
 
     def grad(self):

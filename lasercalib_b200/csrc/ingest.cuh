@@ -3,6 +3,7 @@
 // when needed, narrow int64 indices, build the per-point CSR offsets and visibility masks.
 #pragma once
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include "common.cuh"
 
 namespace lcba {
@@ -74,6 +75,43 @@ __global__ void k_point_masks(const uint8_t* __restrict__ cam, const uint32_t* _
   for (uint32_t i = a; i < b; ++i) m |= 1ull << cam[i];
   mask[p] = m;
   atomicMax(kmax, (int)(b - a));
+}
+
+// ---- repeated (camera, point) rows ------------------------------------------------------
+// The reference accepts any number of rows for one (camera, point) pair (each is one more
+// residual pair; its own 3-dataset concatenation produces them, calibrate_camera.py:41-44).
+// The observation-major passes handle them as they come.  The Schur-side passes work per
+// distinct pair: rows of one pair have the same Jacobian up to their weight, so the pair
+// enters U, W and Y with the weight sqrt(sum w^2).
+__global__ void k_pair_first(const uint8_t* __restrict__ cam, const int32_t* __restrict__ pt,
+                             long long N, int* __restrict__ first) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  first[i] = (i == 0 || cam[i] != cam[i - 1] || pt[i] != pt[i - 1]) ? 1 : 0;
+}
+
+__global__ void k_pair_weights(const int* __restrict__ first, const int* __restrict__ rank,
+                               const double* __restrict__ w, long long N,
+                               double* __restrict__ pair_w) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N || !first[i]) return;
+  double s = 0.0;
+  long long j = i;
+  do {
+    const double wj = w ? w[j] : 1.0;
+    s = fma(wj, wj, s);
+    ++j;
+  } while (j < N && !first[j]);
+  pair_w[rank[i]] = (j == i + 1) ? (w ? w[i] : 1.0) : sqrt(s);
+}
+
+__global__ void k_pair_start(const uint32_t* __restrict__ obs_start, const int* __restrict__ rank,
+                             long long P, long long N, long long n_pairs,
+                             uint32_t* __restrict__ pair_start) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p > P) return;
+  const uint32_t o = obs_start[p];
+  pair_start[p] = (o < N) ? (uint32_t)rank[o] : (uint32_t)n_pairs;
 }
 
 }  // namespace lcba

@@ -10,6 +10,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "common.cuh"
 #include "control.cuh"
 #include "dense.cuh"
@@ -103,7 +105,15 @@ struct lcba_handle {
   // outputs on demand
   double2* d_rout = nullptr;
   double *d_Jc = nullptr, *d_Jp = nullptr;
+  // Schur-side view of the observations: one entry per distinct (point, camera) pair.  Equal to
+  // (d_obs_start, d_w, N) unless the input repeats pairs; then repeated rows are merged into one
+  // entry with the weight sqrt(sum w^2) (same Jacobian rows up to the weight: same U, W, Y).
+  uint32_t* d_pair_start = nullptr;
+  double* d_pair_w = nullptr;
+  long long n_pairs = 0;
   // trace / profile
+  lcba_iteration_cb iter_cb = nullptr;
+  void* iter_cb_user = nullptr;
   std::vector<lcba_trace_row> trace;
   bool prof_on = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -164,6 +174,12 @@ static void dev_free_all(lcba_t* h) {
       pr_.second += ms_;                                              \
     }                                                                 \
   } while (0)
+
+// NVTX range per solver pass (visible in Nsight Systems / ncu --nvtx; free when no tool listens)
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 static int check_launch(lcba_t* h, const char* what) {
   cudaError_t e = cudaGetLastError();
@@ -397,12 +413,44 @@ extern "C" int lcba_set_problem_shard(lcba_t* h, int32_t C, int64_t P, int64_t N
   ING(cudaMemcpyAsync(flags, d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
   ING(cudaStreamSynchronize(st));
   ING(cudaGetLastError());
+  h->d_pair_start = h->d_obs_start;
+  h->d_pair_w = h->d_w;
+  h->n_pairs = N;
+  if (flags[0] & 4) {
+    // repeated (camera, point) rows: distinct-pair view for the Schur-side passes
+    int *t_first = nullptr, *t_rank = nullptr;
+    void* t_scan = nullptr;
+    auto drop = [&]() { void* q[] = {t_first, t_rank, t_scan}; for (void* x : q) if (x) cudaFreeAsync(x, st); };
+    cudaError_t e = cudaMallocAsync(&t_first, N * sizeof(int), st);
+    if (e == cudaSuccess) e = cudaMallocAsync(&t_rank, N * sizeof(int), st);
+    size_t scan_bytes = 0;
+    if (e == cudaSuccess) {
+      k_pair_first<<<nblk(N, 256), 256, 0, st>>>(h->d_cam, h->d_pt, N, t_first);
+      cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, t_first, t_rank, (int)N, st);
+      e = cudaMallocAsync(&t_scan, scan_bytes, st);
+    }
+    if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(t_scan, scan_bytes, t_first, t_rank, (int)N, st);
+    int last[2] = {0, 0};
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&last[0], t_rank + (N - 1), sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&last[1], t_first + (N - 1), sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+      set_error(h, std::string("lcba_set_problem: pair scan: ") + cudaGetErrorString(e));
+      drop(); cleanup();
+      return LCBA_E_CUDA;
+    }
+    h->n_pairs = (long long)last[0] + last[1];
+    h->launches += 4;
+    int rc = dev_alloc(h, &h->d_pair_w, (size_t)h->n_pairs);
+    if (rc == LCBA_OK) rc = dev_alloc(h, &h->d_pair_start, (size_t)P + 1);
+    if (rc != LCBA_OK) { drop(); cleanup(); return rc; }
+    k_pair_weights<<<nblk(N, 256), 256, 0, st>>>(t_first, t_rank, h->d_w, N, h->d_pair_w);
+    k_pair_start<<<nblk(P + 1, 256), 256, 0, st>>>(h->d_obs_start, t_rank, P, N, h->n_pairs, h->d_pair_start);
+    h->launches += 2;
+    drop();
+  }
   cleanup();
 #undef ING
-  if (flags[0] & 4) {
-    set_error(h, "lcba_set_problem: duplicate (camera, point) observation is not supported");
-    return LCBA_E_UNSUPPORTED;
-  }
   h->kmax = flags[1];
   h->B = LIN_THREADS - h->kmax;
   if (h->B < 32) { set_error(h, "lcba_set_problem: too many observations per point"); return LCBA_E_UNSUPPORTED; }
@@ -455,7 +503,7 @@ extern "C" int lcba_set_problem_shard(lcba_t* h, int32_t C, int64_t P, int64_t N
   h->d_mkinds = nullptr; h->d_U = nullptr; h->d_Upart = nullptr; h->d_Yg = nullptr;
   int max_slices = h->plan.nslices;
   {
-    const bool dense = (double)N >= 0.8 * (double)P * C;
+    const bool dense = (double)h->n_pairs >= 0.8 * (double)P * C;
     const char* env = getenv("LCBA_SCHUR_MMA");
     const bool want = env ? atoi(env) != 0 : (dense && C >= 8);
     if (want && C <= MMA_MAX_CAMERAS) {
@@ -624,14 +672,14 @@ static int build_tables(lcba_t* h, int which) {
   return LCBA_OK;
 }
 
-// sum r^2 of buffer set `which` -> d_red[0] (all-reduced); optional residual output
-static int run_residual(lcba_t* h, int which, double2* r_out) {
+// sum r^2 of buffer set `which` -> d_red[0] (all-reduced unless `local`); optional residual output
+static int run_residual(lcba_t* h, int which, double2* r_out, bool local = false) {
   const size_t smem = (size_t)h->C * CAMTAB * 8;
   KL(h, "residual", k_residual<<<h->obs_grid, 256, smem, h->stream>>>(
         h->d_tab[which], h->d_pts[which], h->d_uv, h->d_cam, h->d_pt, h->d_w, h->d_perm, h->N, h->C,
         r_out, h->d_part));
   KL(h, "reduce", k_reduce_scalars<<<1, 256, 0, h->stream>>>(h->d_part, h->obs_grid, 1, h->d_red, 1));
-  return allreduce(h, h->d_red, 1, NCCL_SUM);
+  return local ? LCBA_OK : allreduce(h, h->d_red, 1, NCCL_SUM);
 }
 
 static int upload_x_to(lcba_t* h, const double* x, int which) {
@@ -648,7 +696,7 @@ extern "C" int lcba_residuals(lcba_t* h, const double* x_or_null, double* r_out,
   if (x_or_null) { which = 1 - h->cur; LCBA_TRY(upload_x_to(h, x_or_null, which)); }
   LCBA_TRY(build_tables(h, which));
   if (r_out && !h->d_rout) LCBA_TRY(dev_alloc(h, &h->d_rout, (size_t)h->N));
-  LCBA_TRY(run_residual(h, which, r_out ? h->d_rout : nullptr));
+  LCBA_TRY(run_residual(h, which, r_out ? h->d_rout : nullptr, /*local=*/cost_out == nullptr));
   double ss = 0;
   LCBA_CUDA(h, cudaMemcpyAsync(&ss, h->d_red, 8, cudaMemcpyDeviceToHost, h->stream));
   if (r_out) LCBA_CUDA(h, cudaMemcpyAsync(r_out, h->d_rout, (size_t)h->N * 16, cudaMemcpyDeviceToHost, h->stream));
@@ -691,6 +739,7 @@ extern "C" int lcba_jacobian_blocks(lcba_t* h, const double* x_or_null, double* 
 
 // ------------------------------------------------------------------------------ solver passes
 static int pass_linearize(lcba_t* h, int first) {
+  NvtxRange nvtx_("lcba:linearize");
   const int C = h->C, w = h->cur;
   LCBA_TRY(build_tables(h, w));
   const size_t smem = linearize_smem_doubles(C) * 8;
@@ -716,6 +765,7 @@ static int pass_linearize(lcba_t* h, int first) {
 }
 
 static int pass_jdot(lcba_t* h) {
+  NvtxRange nvtx_("lcba:jdot");
   const int C = h->C, w = h->cur;
   const size_t smem = ((size_t)C * CAMTAB + (size_t)C * NCP) * 8;
   KL(h, "jdot", k_jdot<<<h->obs_grid, 256, smem, h->stream>>>(
@@ -726,27 +776,20 @@ static int pass_jdot(lcba_t* h) {
   return check_launch(h, "jdot pass");
 }
 
-__global__ void k_point_factor_ctl(const double* Vg, const double* scl, const Ctl* ctl, long long P,
-                                   double* Lz);
-__global__ void k_assemble_S_ctl(const double* red, int C, int npairs, const double* camsum,
-                                 const double* scl_c, const Ctl* ctl, double* S, double* rhs);
-
 static int pass_schur(lcba_t* h, const double* lam_host_or_null) {
+  NvtxRange nvtx_("lcba:schur");
   const int C = h->C, w = h->cur, n = C * NCP;
   const SchurPlan& pl = h->plan;
-  if (lam_host_or_null) {
-    KL(h, "point_factor", k_point_factor<<<nblk(h->P, 256), 256, 0, h->stream>>>(
-          h->d_Vg, h->d_scl_p, *lam_host_or_null, h->P, h->d_Lz));
-  } else {
-    KL(h, "point_factor", k_point_factor_ctl<<<nblk(h->P, 256), 256, 0, h->stream>>>(
-          h->d_Vg, h->d_scl_p, h->d_ctl, h->P, h->d_Lz));
-  }
+  const double lam_arg = lam_host_or_null ? *lam_host_or_null : 0.0;
+  const Ctl* ctl_arg = lam_host_or_null ? nullptr : h->d_ctl;
+  KL(h, "point_factor", k_point_factor<<<nblk(h->P, 256), 256, 0, h->stream>>>(
+        h->d_Vg, h->d_scl_p, lam_arg, ctl_arg, h->P, h->d_Lz));
   if (h->use_mma) {
     // dense rigs: SYRK on the FP64 tensor path + the camera blocks U from their own pass
     const MmaPlan& mp = h->mplan;
     const size_t smem_u = ((size_t)((C * CAMTAB + 1) & ~1) + (size_t)h->camn_pb * C) * 8;
     KL(h, "cam_normal", k_cam_normal<<<h->camn_grid, 256, smem_u, h->stream>>>(
-          h->d_tab[w], h->d_pts[w], h->d_w, h->d_obs_start, h->d_mask, h->P, C, h->camn_pb, h->d_Upart));
+          h->d_tab[w], h->d_pts[w], h->d_pair_w, h->d_pair_start, h->d_mask, h->P, C, h->camn_pb, h->d_Upart));
     KL(h, "reduce", k_reduce_cols<<<nblk(C * CAMN_VALS, RC_COLS), RC_COLS * RC_ROWS, 0, h->stream>>>(
           h->d_Upart, h->camn_grid, C * CAMN_VALS, h->d_U));
     const int nt = (NCP * C + 1 + 7) / 8, last = nt - 6 * ((nt + 5) / 6 - 1);
@@ -755,18 +798,18 @@ static int pass_schur(lcba_t* h, const double* lam_host_or_null) {
       const size_t smem_y = ((size_t)((C * CAMTAB + 1) & ~1) + (size_t)3 * pbk * rpk) * 8;
       const int grid_y = (int)std::min<long long>((h->P + pbk - 1) / pbk, (long long)h->sm_count * 5);
       KL(h, "make_Y", k_make_Y<<<grid_y, MAKEY_THREADS, smem_y, h->stream>>>(
-            h->d_tab[w], h->d_pts[w], h->d_w, h->d_obs_start, h->d_mask, h->d_Lz, h->P, C, mp.kinds[0].rp,
+            h->d_tab[w], h->d_pts[w], h->d_pair_w, h->d_pair_start, h->d_mask, h->d_Lz, h->P, C, mp.kinds[0].rp,
             h->d_Yg));
     }
 #define LCBA_MMA_LAUNCH(L)                                                                          \
   do {                                                                                              \
     if (h->d_Yg)                                                                                    \
       KL(h, "schur", (k_schur_mma<L, true><<<dim3(mp.nslices, mp.nkinds), MMA_THREADS, mp.smem_bytes, h->stream>>>( \
-            h->d_Yg, h->d_tab[w], h->d_pts[w], h->d_w, h->d_obs_start, h->d_mask, h->d_Lz, h->P, h->N, C, \
+            h->d_Yg, h->d_tab[w], h->d_pts[w], h->d_pair_w, h->d_pair_start, h->d_mask, h->d_Lz, h->P, h->n_pairs, C, \
             h->d_mkinds, mp.nslices, pl.part_stride, pl.npairs, h->d_Spart, h->d_stats)));          \
     else                                                                                            \
       KL(h, "schur", (k_schur_mma<L, false><<<dim3(mp.nslices, mp.nkinds), MMA_THREADS, mp.smem_bytes, h->stream>>>( \
-            nullptr, h->d_tab[w], h->d_pts[w], h->d_w, h->d_obs_start, h->d_mask, h->d_Lz, h->P, h->N, C, \
+            nullptr, h->d_tab[w], h->d_pts[w], h->d_pair_w, h->d_pair_start, h->d_mask, h->d_Lz, h->P, h->n_pairs, C, \
             h->d_mkinds, mp.nslices, pl.part_stride, pl.npairs, h->d_Spart, h->d_stats)));          \
   } while (0)
     switch (last) {
@@ -784,10 +827,10 @@ static int pass_schur(lcba_t* h, const double* lam_host_or_null) {
   } else {
   dim3 grid(pl.nslices, pl.nkinds);
   // sparse rigs skip duo blocks nobody sees; dense rigs run branch-free
-  const bool skip = (double)h->N < 0.8 * (double)h->P * C;
+  const bool skip = (double)h->n_pairs < 0.8 * (double)h->P * C;
 #define LCBA_SCHUR_LAUNCH(SK, NR)                                                                   \
   KL(h, "schur", (k_schur<SK, NR><<<grid, pl.max_threads, pl.smem_bytes, h->stream>>>(              \
-        h->d_tab[w], h->d_pts[w], h->d_w, h->d_obs_start, h->d_mask, h->d_Lz, h->P, h->N, C,        \
+        h->d_tab[w], h->d_pts[w], h->d_pair_w, h->d_pair_start, h->d_mask, h->d_Lz, h->P, h->n_pairs, C, \
         h->d_kinds, h->d_hws, pl.nslices, pl.part_stride, pl.npairs, h->d_Spart, h->d_stats)))
   if (pl.cfg != 1) { if (skip) LCBA_SCHUR_LAUNCH(true, 160); else LCBA_SCHUR_LAUNCH(false, 160); }
   else             { if (skip) LCBA_SCHUR_LAUNCH(true, 128); else LCBA_SCHUR_LAUNCH(false, 128); }
@@ -802,74 +845,16 @@ static int pass_schur(lcba_t* h, const double* lam_host_or_null) {
           h->d_Sred, C, pl.npairs, h->d_camsum, h->d_scl_c, h->d_ctl,
           lam_host_or_null ? *lam_host_or_null : 0.0, lam_host_or_null ? 0 : 1, h->d_S, h->d_rhs,
           h->d_scl_red));
-  } else if (lam_host_or_null) {
-    KL(h, "assemble", k_assemble_S<<<nblk((long long)n * n, 256), 256, 0, h->stream>>>(
-          h->d_Sred, C, pl.npairs, h->d_camsum, h->d_scl_c, *lam_host_or_null, h->d_S, h->d_rhs));
   } else {
-    KL(h, "assemble", k_assemble_S_ctl<<<nblk((long long)n * n, 256), 256, 0, h->stream>>>(
-          h->d_Sred, C, pl.npairs, h->d_camsum, h->d_scl_c, h->d_ctl, h->d_S, h->d_rhs));
+    KL(h, "assemble", k_assemble_S<<<nblk((long long)n * n, 256), 256, 0, h->stream>>>(
+          h->d_Sred, C, pl.npairs, h->d_camsum, h->d_scl_c, lam_arg, ctl_arg, h->d_S, h->d_rhs));
   }
   return check_launch(h, "schur pass");
 }
 
-// lambda read from the device control block (no host round trip)
-__global__ void __launch_bounds__(256)
-k_point_factor_ctl(const double* __restrict__ Vg, const double* __restrict__ scl,
-                   const Ctl* __restrict__ ctl, long long P, double* __restrict__ Lz) {
-  // same arithmetic as k_point_factor; kept as a thin wrapper through a device call
-  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= P) return;
-  const double lam = ctl->reg_term;
-  const double* v = Vg + p * 9;
-  const double s0 = scl[3 * p], s1 = scl[3 * p + 1], s2 = scl[3 * p + 2];
-  const double v00 = fma(lam * s0, s0, v[0]), v11 = fma(lam * s1, s1, v[3]), v22 = fma(lam * s2, s2, v[5]);
-  const double v01 = v[1], v02 = v[2], v12 = v[4];
-  const double tiny = 1e-300;
-  const double l00 = sqrt(fmax(v00, tiny));
-  const double i00 = 1.0 / l00;
-  const double l10 = v01 * i00, l20 = v02 * i00;
-  const double d11 = v11 - l10 * l10;
-  const double l11 = sqrt(fmax(d11, fmax(1e-14 * v11, tiny)));
-  const double i11 = 1.0 / l11;
-  const double l21 = (v12 - l20 * l10) * i11;
-  const double d22 = v22 - l20 * l20 - l21 * l21;
-  const double l22 = sqrt(fmax(d22, fmax(1e-14 * v22, tiny)));
-  const double i22 = 1.0 / l22;
-  const double i10 = -l10 * i00 * i11;
-  const double i21 = -l21 * i11 * i22;
-  const double i20 = -(l20 * i00 + l21 * i10) * i22;
-  double* o = Lz + p * 9;
-  o[0] = i00; o[1] = i10; o[2] = i11; o[3] = i20; o[4] = i21; o[5] = i22;
-  const double g0 = v[6], g1 = v[7], g2 = v[8];
-  o[6] = i00 * g0;
-  o[7] = fma(i10, g0, i11 * g1);
-  o[8] = fma(i20, g0, fma(i21, g1, i22 * g2));
-}
-
-__global__ void k_assemble_S_ctl(const double* __restrict__ red, int C, int npairs,
-                                 const double* __restrict__ camsum, const double* __restrict__ scl_c,
-                                 const Ctl* __restrict__ ctl, double* __restrict__ S,
-                                 double* __restrict__ rhs) {
-  const double lam = ctl->reg_term;
-  const int n = C * NCP;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)n * n) return;
-  const int r = (int)(idx / n), c = (int)(idx % n);
-  const int hi = max(r, c), lo = min(r, c);
-  const int j = hi / NCP, a = hi % NCP, k = lo / NCP, b = lo % NCP;
-  double v;
-  if (j == k) v = red[(size_t)(j * (j + 1) / 2 + j) * 121 + (r % NCP) * NCP + (c % NCP)];
-  else v = red[(size_t)(j * (j + 1) / 2 + k) * 121 + a * NCP + b];
-  if (r == c) {
-    const double s = scl_c[r];
-    v = fma(lam * s, s, v);
-    rhs[r] = camsum[(r / NCP) * 22 + (r % NCP)] + red[(size_t)npairs * 121 + r];
-  }
-  S[idx] = v;
-}
-
 // Cholesky of S + mu*Dc^2, solve for the camera step
 static int pass_camera_solve(lcba_t* h, double mu) {
+  NvtxRange nvtx_("lcba:camera_solve");
   const int n = h->shared_intr ? 3 + 8 * h->C : h->C * NCP;
   LCBA_CUDA(h, cudaMemsetAsync(h->d_fail, 0, 2 * sizeof(int), h->stream));
   const double* scl = h->shared_intr ? h->d_scl_red : h->d_scl_c;
@@ -914,6 +899,7 @@ static int pass_camera_solve(lcba_t* h, double mu) {
 }
 
 static int pass_backsub(lcba_t* h) {
+  NvtxRange nvtx_("lcba:backsub");
   const int C = h->C, w = h->cur;
   const size_t smem = ((size_t)C * CAMTAB + 2 * (size_t)C * NCP + 2 * LIN_THREADS * 3) * 8;
   KL(h, "backsub", k_backsub<<<h->lin_grid, LIN_THREADS, smem, h->stream>>>(
@@ -927,6 +913,7 @@ static int pass_backsub(lcba_t* h) {
 }
 
 static int pass_trial(lcba_t* h) {
+  NvtxRange nvtx_("lcba:trial");
   const int w = h->cur, t = 1 - h->cur;
   const long long nc = (long long)h->C * NCP, np = h->P * 3;
   KL(h, "make_trial", k_make_trial<<<1, 256, 0, h->stream>>>(h->d_cams[w], h->d_gt_c, h->d_pc, h->d_coef, nc,
@@ -952,6 +939,14 @@ static void add_trace(lcba_t* h, long long it, long long nfev, double cost, doub
   r.iteration = it; r.nfev = nfev; r.cost = cost; r.cost_reduction = red; r.step_norm = step;
   r.optimality = opt; r.delta = delta; r.reg_term = reg;
   h->trace.push_back(r);
+  if (h->iter_cb) h->iter_cb(&h->trace.back(), h->iter_cb_user);
+}
+
+extern "C" int lcba_set_iteration_callback(lcba_t* h, lcba_iteration_cb cb, void* user) {
+  if (!h) return LCBA_E_ARG;
+  h->iter_cb = cb;
+  h->iter_cb_user = user;
+  return LCBA_OK;
 }
 
 extern "C" int lcba_solve(lcba_t* h, const lcba_options* opt_in, lcba_result* res) {
@@ -979,9 +974,12 @@ extern "C" int lcba_solve(lcba_t* h, const lcba_options* opt_in, lcba_result* re
   const long long n_total = n_cam + 3 * h->P_total;
   const long long max_nfev = opt.max_nfev > 0 ? opt.max_nfev : 100 * n_total;
 
-  cudaEvent_t t0, t1;
-  cudaEventCreate(&t0);
-  cudaEventCreate(&t1);
+  struct EventPair {   // destroyed on every exit path
+    cudaEvent_t a = nullptr, b = nullptr;
+    EventPair() { cudaEventCreate(&a); cudaEventCreate(&b); }
+    ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+  } ev;
+  cudaEvent_t t0 = ev.a, t1 = ev.b;
   cudaEventRecord(t0, h->stream);
 
   Ctl init;
@@ -995,7 +993,6 @@ extern "C" int lcba_solve(lcba_t* h, const lcba_options* opt_in, lcba_result* re
   LCBA_TRY(read_ctl(h));
   if (h->h_ctl->nonfinite) {
     set_error(h, "Residuals are not finite in the initial point.");
-    cudaEventDestroy(t0); cudaEventDestroy(t1);
     return LCBA_E_NONFINITE;
   }
   long long nfev = 1, njev = 1, iteration = 0;
@@ -1028,8 +1025,8 @@ extern "C" int lcba_solve(lcba_t* h, const lcba_options* opt_in, lcba_result* re
     LCBA_TRY(pass_jdot(h));
     if (h->fix_cameras) {
       // points only: the normal equations are block diagonal, p_p = (V + lam Dp^2)^-1 g_p
-      KL(h, "point_factor", k_point_factor_ctl<<<nblk(h->P, 256), 256, 0, h->stream>>>(
-            h->d_Vg, h->d_scl_p, h->d_ctl, h->P, h->d_Lz));
+      KL(h, "point_factor", k_point_factor<<<nblk(h->P, 256), 256, 0, h->stream>>>(
+            h->d_Vg, h->d_scl_p, 0.0, h->d_ctl, h->P, h->d_Lz));
       LCBA_CUDA(h, cudaMemsetAsync(h->d_pc, 0, (size_t)h->C * NCP * 8, h->stream));
       LCBA_CUDA(h, cudaMemsetAsync(h->d_fail, 0, 2 * sizeof(int), h->stream));
     } else {
@@ -1054,14 +1051,12 @@ extern "C" int lcba_solve(lcba_t* h, const lcba_options* opt_in, lcba_result* re
       }
       if (h->h_ctl->chol_fail & 2) {
         set_error(h, "k_chol_fused: grid barrier timed out");
-        cudaEventDestroy(t0); cudaEventDestroy(t1);
         return LCBA_E_CUDA;
       }
       if (h->h_ctl->retry) {
         mu = std::max(std::max(10.0 * mu, 10.0 * h->h_ctl->reg_term), 1e-13);
         if (mu > 1e6) {
           set_error(h, "reduced camera system is not positive definite even with damping");
-          cudaEventDestroy(t0); cudaEventDestroy(t1);
           return LCBA_E_NONFINITE;
         }
         continue;
@@ -1108,8 +1103,6 @@ extern "C" int lcba_solve(lcba_t* h, const lcba_options* opt_in, lcba_result* re
   cudaEventSynchronize(t1);
   float ms = 0;
   cudaEventElapsedTime(&ms, t0, t1);
-  cudaEventDestroy(t0);
-  cudaEventDestroy(t1);
   res->cost = cost;
   res->optimality = g_norm;
   res->nfev = nfev;

@@ -10,6 +10,7 @@
 // observation; per-point reductions go through shared memory (deterministic, no atomics).
 #pragma once
 #include "common.cuh"
+#include "control.cuh"
 
 namespace lcba {
 
@@ -281,12 +282,14 @@ k_jdot(const double* __restrict__ tab, const double* __restrict__ pts,
 // Lz[p][0..5] = L^-1 (00,10,11,20,21,22), Lz[p][6..8] = z = L^-1 g_p, with
 // L L^T = V + lam * diag(scl^2).  Pivots are clamped so that points with < 2 views
 // (rank-deficient V; never produced by the reference's pipeline, get_points3d.py:52-56)
-// give finite numbers.
+// give finite numbers.  lam comes from the device control block (solver loop: no host round
+// trip) when `ctl` is given, from the argument otherwise (lcba_linearize debug tap).
 __global__ void __launch_bounds__(256)
 k_point_factor(const double* __restrict__ Vg, const double* __restrict__ scl, double lam,
-               long long P, double* __restrict__ Lz) {
+               const Ctl* __restrict__ ctl, long long P, double* __restrict__ Lz) {
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
+  if (ctl) lam = ctl->reg_term;
   const double* v = Vg + p * 9;
   const double s0 = scl[3 * p], s1 = scl[3 * p + 1], s2 = scl[3 * p + 2];
   const double v00 = fma(lam * s0, s0, v[0]), v11 = fma(lam * s1, s1, v[3]),

@@ -488,10 +488,13 @@ k_schur(const double* __restrict__ tab, const double* __restrict__ pts,
   }
 }
 
-// S (n x n, both triangles) = reduced blocks + lam * diag(scl_c^2) ; rhs = g_c + rhs_red
+// S (n x n, both triangles) = reduced blocks + lam * diag(scl_c^2) ; rhs = g_c + rhs_red.
+// lam: the device control block's reg_term when `ctl` is given, the argument otherwise.
 __global__ void k_assemble_S(const double* __restrict__ red, int C, int npairs,
                              const double* __restrict__ camsum, const double* __restrict__ scl_c,
-                             double lam, double* __restrict__ S, double* __restrict__ rhs) {
+                             double lam, const Ctl* __restrict__ ctl, double* __restrict__ S,
+                             double* __restrict__ rhs) {
+  if (ctl) lam = ctl->reg_term;
   const int n = C * NCP;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)n * n) return;

@@ -58,18 +58,23 @@ def shard_bounds(point_ind, n_points, nranks):
     return b
 
 
-_sorted_cache = {}     # (data pointer, size) -> bool, so repeated calls on the same array are O(1)
-
-
 def _is_point_major(point_ind):
-    key = (point_ind.ctypes.data, point_ind.size, point_ind.dtype.str)
-    hit = _sorted_cache.get(key)
-    if hit is None:
-        hit = bool(point_ind.size < 2 or np.all(point_ind[1:] >= point_ind[:-1]))
-        if len(_sorted_cache) > 64:
-            _sorted_cache.clear()
-        _sorted_cache[key] = hit
-    return hit
+    """O(N) monotonicity check, every time: a cached answer keyed on the buffer address could be
+    stale for a different or mutated array that reuses the address."""
+    return bool(point_ind.size < 2 or np.all(point_ind[1:] >= point_ind[:-1]))
+
+
+def _check_shards(bounds, counts_fn, nranks):
+    """Every rank derives the same bounds from the same global arrays, so every rank reaches
+    the same verdict here BEFORE any collective: an empty shard (more ranks than points that
+    have observations, or badly skewed bounds) raises on all ranks instead of failing one rank
+    inside set_problem while the others wait in NCCL."""
+    for r in range(nranks):
+        npts = int(bounds[r + 1] - bounds[r])
+        nobs = counts_fn(r)
+        if npts <= 0 or nobs <= 0:
+            raise ValueError("point sharding over %d ranks leaves rank %d without work (%d points, %d "
+                             "observations): use fewer ranks" % (nranks, r, npts, nobs))
 
 
 def shard_problem(points3D, points2D, camera_ind, point_ind, weights, rank, nranks, bounds=None):
@@ -89,9 +94,11 @@ def shard_problem(points3D, points2D, camera_ind, point_ind, weights, rank, nran
         for r in range(1, nranks):
             b[r] = int(point_ind[min(N - 1, (N * r) // nranks)]) + (1 if N * r // nranks > 0 else 0)
         b = np.minimum(np.maximum.accumulate(b), P)
+        cuts = np.searchsorted(point_ind, b, side="left")
+        cuts[nranks] = N
+        _check_shards(b, lambda r: int(cuts[r + 1] - cuts[r]), nranks)
         lo, hi = int(b[rank]), int(b[rank + 1])
-        o0 = int(np.searchsorted(point_ind, lo, side="left"))
-        o1 = int(np.searchsorted(point_ind, hi, side="left"))
+        o0, o1 = int(cuts[rank]), int(cuts[rank + 1])
         w = None if weights is None else np.asarray(weights).reshape(-1)[o0:o1]
         return dict(pts=np.ascontiguousarray(points3D[lo:hi]),
                     points_2d=np.asarray(points2D)[o0:o1],
@@ -100,6 +107,9 @@ def shard_problem(points3D, points2D, camera_ind, point_ind, weights, rank, nran
                     weights=w, lo=lo, hi=hi, obs_sel=slice(o0, o1), bounds=b)
     if bounds is None:
         bounds = shard_bounds(point_ind, P, nranks)
+    owner = np.searchsorted(np.asarray(bounds)[1:], point_ind, side="right")
+    per_rank = np.bincount(owner, minlength=nranks)
+    _check_shards(bounds, lambda r: int(per_rank[r]), nranks)
     lo, hi = int(bounds[rank]), int(bounds[rank + 1])
     sel = np.nonzero((point_ind >= lo) & (point_ind < hi))[0]
     w = None if weights is None else np.asarray(weights).reshape(-1)[sel]

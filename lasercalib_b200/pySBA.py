@@ -47,6 +47,15 @@ class BAResult(OptimizeResult):
     def set_lazy(self, key, fn):
         self._lazy[key] = fn
 
+    def __contains__(self, key):
+        return dict.__contains__(self, key) or key in object.__getattribute__(self, "_lazy")
+
+    def keys(self):
+        return list(dict.keys(self)) + [k for k in self._lazy if not dict.__contains__(self, k)]
+
+    def __dir__(self):
+        return self.keys()
+
     def __missing__(self, key):
         lazy = object.__getattribute__(self, "_lazy")
         if key in lazy:
@@ -99,8 +108,12 @@ class PySBA:
         self.points3Dfixed_labeled = None
         self._engine = None
         self._problem_key = None
+        self._owner_token = None
         self._fresh_problem = True
         self.last_trace = None
+        # engine knob (not in the reference): True = the observation arrays are promised not to
+        # change, so their device copy is reused between calls; default = re-read every call
+        self.observations_static = False
 
     @property
     def pointWeights(self):
@@ -118,7 +131,9 @@ class PySBA:
         d = dict(self.__dict__)
         d["_engine"] = None
         d["_problem_key"] = None
+        d["_owner_token"] = None
         d.pop("_keep", None)
+        d.pop("_shard", None)
         return d
 
     def __setstate__(self, d):
@@ -136,46 +151,48 @@ class PySBA:
                 eng = _cabi.Engine(dev)
                 eng._comm_ready = False
                 eng._owner = None
+                eng._owner_token = None
                 _ENGINES[dev] = eng
             self._engine = eng
         return self._engine
 
     def _weights_arg(self, pointWeights):
         if pointWeights is None or (self._default_weights and pointWeights is self._pointWeights):
-            n = np.asarray(self.point2DIndices).size
-            return None, ("ones", n)
+            return None
         w = np.asarray(pointWeights).reshape(-1)
         if w.dtype.kind in "iu" and np.all(w == 1):
-            return None, ("ones", w.size)
-        wf = np.ascontiguousarray(w, dtype=np.float64)
-        return wf, ("w", wf.ctypes.data, wf.size, float(wf[:8].sum()))
+            return None
+        return np.ascontiguousarray(w, dtype=np.float64)
 
-    @staticmethod
-    def _fingerprint(a):
-        """Cheap content signature (64 strided samples + their sum) so that an observation
-        array edited in place is re-uploaded instead of served from the resident copy."""
-        flat = a.reshape(-1)
-        if flat.size == 0:
-            return (0,)
-        smp = flat[:: max(1, flat.size // 64)][:64]
-        return (flat.size, float(smp.sum()), float(flat[-1]))
+    def invalidate(self):
+        """Forget the device-resident copy of the observation arrays (only meaningful with
+        ``observations_static = True``): the next call uploads them again."""
+        self._problem_key = None
 
     def _ensure_problem(self, cams, pts, camera_indices, point_indices, points_2d, pointWeights):
-        """(Re)load the observation set on the device unless it is already resident."""
+        """Load the observation set on the device.
+
+        Like the reference, every call reads the caller's arrays again (an in-place edit of
+        ``points2D`` / ``pointWeights`` / the index arrays between two calls is honoured).
+        Set ``sba.observations_static = True`` to promise that those arrays do not change
+        while this object lives: the device copy is then reused as long as the same array
+        objects are passed (`invalidate()` drops it)."""
         eng = self._get_engine()
-        w, wkey = self._weights_arg(pointWeights)
+        w = self._weights_arg(pointWeights)
         ci = np.asarray(camera_indices)
         pi = np.asarray(point_indices)
         p2 = np.asarray(points_2d)
         key = (cams.shape[0], pts.shape[0], ci.ctypes.data, ci.size, pi.ctypes.data,
-               p2.ctypes.data, wkey, self._fingerprint(ci), self._fingerprint(pi),
-               self._fingerprint(p2))
-        self._fresh_problem = key != self._problem_key or eng._owner is not self
+               p2.ctypes.data, None if w is None else (w.ctypes.data, w.size))
+        reuse = (self.observations_static and key == self._problem_key and eng._owner is self
+                 and eng._owner_token == self._owner_token)
+        self._fresh_problem = not reuse
         if self._fresh_problem:
             eng.set_problem(cams, pts, p2, ci, pi, w)
             eng._owner = self
+            self._owner_token = eng._owner_token = object()
             self._problem_key = key
-            self._keep = (ci, pi, p2, w)       # keep the keyed buffers alive
+            self._keep = (ci, pi, p2, w, pointWeights)   # keep the keyed buffers alive
         return eng
 
     # ---- model (pySBA.py:61-89) ----
@@ -240,14 +257,26 @@ class PySBA:
         if ws > 1:
             # one process per GPU: this rank keeps a contiguous range of points and their
             # observations; cameras are replicated; the library all-reduces with NCCL
-            w, _ = self._weights_arg(self._pointWeights)
-            shard = _dist.shard_problem(pts0, self.points2D, self.cameraIndices,
-                                        self.point2DIndices, w, rank, ws)
+            w = self._weights_arg(self._pointWeights)
             eng = self._get_engine()
-            eng.set_problem(cams0, shard["pts"], shard["points_2d"], shard["camera_ind"],
-                            shard["point_ind"], shard["weights"], pt_offset=shard["pt_offset"])
-            self._problem_key = None
-            eng._owner = self
+            key = ("shard", ws, cams0.shape[0], pts0.shape[0], id(self.points2D),
+                   id(self.cameraIndices), id(self.point2DIndices), None if w is None else id(self._pointWeights))
+            reuse = (self.observations_static and key == self._problem_key and eng._owner is self
+                     and eng._owner_token == self._owner_token)
+            if reuse:
+                shard = self._shard
+                eng.set_params(cams0, shard["pts0_of"](pts0))
+            else:
+                shard = _dist.shard_problem(pts0, self.points2D, self.cameraIndices,
+                                            self.point2DIndices, w, rank, ws)
+                lo, hi = shard["lo"], shard["hi"]
+                shard["pts0_of"] = lambda p, lo=lo, hi=hi: np.ascontiguousarray(p[lo:hi])
+                eng.set_problem(cams0, shard["pts"], shard["points_2d"], shard["camera_ind"],
+                                shard["point_ind"], shard["weights"], pt_offset=shard["pt_offset"])
+                self._problem_key = key
+                self._shard = shard
+                eng._owner = self
+                self._owner_token = eng._owner_token = object()
             if not eng._comm_ready:
                 _dist.connect_engine(eng)
                 eng._comm_ready = True
@@ -258,20 +287,21 @@ class PySBA:
                                        self.points2D, self._pointWeights)
             if not self._fresh_problem or _shared:   # observations already resident: new x0 only
                 eng.set_params(cams0, pts0)
+        live = None
+        if verbose == 2:
+            # scipy prints the table while it iterates (least_squares(verbose=2), pySBA.py:141)
+            _print_header()
+            live = _print_row
         try:
             res, trace = eng.solve(ftol=ftol, xtol=xtol, gtol=gtol, max_nfev=max_nfev or 0,
                                    verbose=verbose, profile=profile,
                                    max_iterations=max_iterations, fix_cameras=_fix_cameras,
-                                   shared_intrinsics=_shared)
+                                   shared_intrinsics=_shared, on_iteration=live)
         except _cabi.LcbaError as e:
             if e.code == -5:
                 raise ValueError("Residuals are not finite in the initial point.") from e
             raise
         self.last_trace = trace
-        if verbose == 2:
-            _print_header()
-            for row in trace:
-                _print_row(row)
         x_direct = None
         nc = numCameras * N_CAM_PARAMS
         if not _fix_cameras and not _shared:
@@ -287,8 +317,38 @@ class PySBA:
                 pts = _dist.allgather_rows(pts, shard["bounds"], out=x_direct[nc:].reshape(numPoints, 3))
             else:
                 pts = _dist.allgather_rows(pts, shard["bounds"])
+        # ---- lazy members: the engine is shared (one handle per device), so by the time
+        # `res.fun` / `res.grad` / `res.jac` are read it may hold another problem or another x.
+        # The readers check the handle's generation counter and, if it moved, put this result's
+        # observation set and final x back before evaluating.  On a point-sharded run the
+        # residual read is local to the rank (no collective), and a stale handle raises: the
+        # other ranks could not follow a re-upload.
+        gen, token = eng.generation, self._owner_token
+        kept = getattr(self, "_keep", None)
+        cams_f, pts_f = cams, pts
+
+        def engine_at_result():
+            if eng.h is not None and eng.generation == gen and eng._owner_token is token:
+                return eng
+            if shard is not None:
+                raise RuntimeError("the engine was used again before this member of a point-sharded "
+                                   "result was read; read res.fun right after bundleAdjust")
+            ci_k, pi_k, p2_k, w_k, _ = kept
+            e = self._get_engine()
+            e.set_problem(np.ascontiguousarray(cams_f), np.ascontiguousarray(pts_f), p2_k, ci_k, pi_k, w_k)
+            e._owner, e._owner_token = None, None
+            self._problem_key = None
+            return e
+
+        def lazy_fun():
+            return engine_at_result().residuals(None, want_cost=False)[0]
+
+        def lazy_grad():
+            e = engine_at_result()
+            return e.grad() if e.generation == gen else e.linearize(1.0)["grad"]
+
         if _fix_cameras:
-            return self._finish_nocam(eng, res, pts, shard, verbose)
+            return self._finish_nocam(lazy_fun, lazy_grad, res, pts, shard, verbose)
         if _shared:
             # the reference's parameter order: [f k1 k2 | extrinsics | centroids | points]
             x = np.hstack((cams[0, 6:9], cams[:, :6].ravel(), cams[:, 9:].ravel(), pts.ravel()))
@@ -299,7 +359,7 @@ class PySBA:
             out["success"] = int(res.status) > 0
             out["solve_ms"] = res.solve_ms
             out["nit"] = int(res.iterations)
-            out.set_lazy("fun", lambda: eng.residuals(None)[0])
+            out.set_lazy("fun", lazy_fun)
             if verbose >= 1:
                 print(out["message"])
             self.cameraArray = cams
@@ -319,18 +379,18 @@ class PySBA:
             # sharded run: `fun` / `grad` / `jac` are this rank's shard (observations
             # `fun_obs_index` of the caller's arrays); x, cost, optimality are global
             out["fun_obs_index"] = shard["obs_sel"]
-            out.set_lazy("fun", lambda: eng.residuals(None)[0])
+            out.set_lazy("fun", lazy_fun)
             if verbose >= 1:
                 print(out["message"])
             camera_params, points_3d = self.optimizedParams(x, numCameras, numPoints)
             self.cameraArray = camera_params
             self.points3D = points_3d
             return out
-        out.set_lazy("grad", eng.grad)
-        out.set_lazy("fun", lambda: eng.residuals(None)[0])
+        out.set_lazy("grad", lazy_grad)
+        out.set_lazy("fun", lazy_fun)
 
         def _jac():
-            Jc, Jp = eng.jacobian_blocks(None)
+            Jc, Jp = engine_at_result().jacobian_blocks(None)
             A = self.bundle_adjustment_sparsity(numCameras, numPoints, ci, pi)
             return csr_matrix((np.concatenate([Jc, Jp], axis=2).ravel(), A.indices, A.indptr),
                               shape=A.shape)
@@ -398,7 +458,7 @@ class PySBA:
         out.set_lazy("fun", lambda: self._squared_fun(cams, pts))
         return out
 
-    def _finish_nocam(self, eng, res, pts, shard, verbose):
+    def _finish_nocam(self, lazy_fun, lazy_grad, res, pts, shard, verbose):
         x = pts.ravel().copy()
         out = BAResult(x=x, cost=res.cost, optimality=res.optimality,
                        active_mask=np.zeros_like(x), nfev=int(res.nfev), njev=int(res.njev),
@@ -408,10 +468,10 @@ class PySBA:
         out["solve_ms"] = res.solve_ms
         out["nit"] = int(res.iterations)
         out["gpu_launches"] = int(res.gpu_launches)
-        out.set_lazy("fun", lambda: eng.residuals(None)[0])
+        out.set_lazy("fun", lazy_fun)
         if shard is None:
             nc = self.cameraArray.shape[0] * N_CAM_PARAMS
-            out.set_lazy("grad", lambda: eng.grad()[nc:])
+            out.set_lazy("grad", lambda: lazy_grad()[nc:])
         else:
             out["fun_obs_index"] = shard["obs_sel"]
         if verbose >= 1:

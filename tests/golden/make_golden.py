@@ -258,11 +258,30 @@ def golden_io():
                              cv2.FILE_STORAGE_READ)
         raw.append((fs.getNode("camera_matrix").mat(), fs.getNode("distortion_coefficients").mat(),
                     fs.getNode("rc_ext").mat(), fs.getNode("tc_ext").mat()))
+    # the reference's YAML export (convert_params.py:105-113) and its own loader on those files
+    import tempfile
+    from lasercalib.convert_params import initialize_from_checkerboard, readable_format_to_aruco_format
+    names = [str(x) for x in g["cam_names"]]
+    with tempfile.TemporaryDirectory() as td:
+        readable_format_to_aruco_format(td + "/", len(names), readable, names)
+        aruco = []
+        for n in names:
+            fs = cv2.FileStorage("%s/%s.yaml" % (td, n), cv2.FILE_STORAGE_READ)
+            aruco.append((fs.getNode("camera_matrix").mat(), fs.getNode("distortion_coefficients").mat(),
+                          fs.getNode("rc_ext").mat(), fs.getNode("tc_ext").mat()))
+        aruco_text0 = open("%s/%s.yaml" % (td, names[0])).read()
+        reloaded = initialize_from_checkerboard(td, len(names), names)
+    init_cams = initialize_from_checkerboard("/root/reference/example/calib_init_2024_05_02", len(names), names)
     np.savez_compressed(os.path.join(HERE, "io_example17.npz"), cams=cams,
                         K=np.array([r["K"] for r in readable]), R=np.array([r["R"] for r in readable]),
                         red=red, camera_matrix=np.array([r[0] for r in raw]),
                         distortion=np.array([r[1] for r in raw]), rc_ext=np.array([r[2] for r in raw]),
-                        tc_ext=np.array([r[3] for r in raw]), **VERS)
+                        tc_ext=np.array([r[3] for r in raw]),
+                        aruco_camera_matrix=np.array([r[0] for r in aruco]),
+                        aruco_distortion=np.array([r[1] for r in aruco]),
+                        aruco_rc_ext=np.array([r[2] for r in aruco]), aruco_tc_ext=np.array([r[3] for r in aruco]),
+                        aruco_text0=np.array(aruco_text0), aruco_reloaded_cams=reloaded, init_cams=init_cams,
+                        cam_names=np.array(names), **VERS)
 
 
 def golden_unproject():

@@ -69,6 +69,35 @@ def test_shard_bounds_properties():
     assert b[0] == 0 and b[-1] == 2 and np.all(np.diff(b) >= 0)
 
 
+def test_sortedness_is_checked_on_every_call():
+    """The point-major fast path must not trust a cached verdict for a reused buffer address:
+    sort an array in place -> unsorted content at the same address gets the general path."""
+    rng = np.random.default_rng(0)
+    P, ws = 50, 2
+    pi = np.repeat(np.arange(P), 3)
+    ci = np.tile(np.arange(3), P)
+    uv = rng.normal(size=(pi.size, 2))
+    pts = rng.normal(size=(P, 3))
+    a = D.shard_problem(pts, uv, ci, pi, None, 0, ws)
+    assert isinstance(a["obs_sel"], slice)
+    perm = rng.permutation(pi.size)
+    pi[:] = pi[perm]                                   # same buffer, now unsorted
+    seen = np.zeros(pi.size, dtype=int)
+    for r in range(ws):
+        sh = D.shard_problem(pts, uv[perm], ci[perm], pi, None, r, ws)
+        assert not isinstance(sh["obs_sel"], slice)
+        np.testing.assert_array_equal(pi[sh["obs_sel"]], sh["point_ind"] + sh["lo"])
+        seen[sh["obs_sel"]] += 1
+    assert np.all(seen == 1)
+
+
+def test_empty_shard_is_refused_on_all_ranks():
+    pi = np.array([0, 0, 1, 1])
+    for r in range(8):
+        with pytest.raises(ValueError, match="without work"):
+            D.shard_problem(np.zeros((2, 3)), np.zeros((4, 2)), np.zeros(4, dtype=int), pi, None, r, 8)
+
+
 def test_world_defaults_to_single_process():
     assert D.world() == (0, 1, 0)
 
@@ -92,8 +121,21 @@ def test_shard_problem_properties_hypothesis():
         pts = rng.normal(size=(P, 3))
         seen = np.zeros(pi.size, dtype=int)
         covered = np.zeros(P, dtype=int)
+        # a sharding that leaves some rank without work is refused on EVERY rank alike (each rank
+        # derives the same bounds), so no rank can fail alone while the others wait in NCCL
+        verdicts = []
+        for r in range(ws):
+            try:
+                D.shard_problem(pts, uv, ci, pi, None, r, ws)
+                verdicts.append(True)
+            except ValueError:
+                verdicts.append(False)
+        assert len(set(verdicts)) == 1
+        if not verdicts[0]:
+            return
         for r in range(ws):
             sh = D.shard_problem(pts, uv, ci, pi, None, r, ws)
+            assert sh["point_ind"].size > 0 and sh["pts"].shape[0] > 0
             local = sh["point_ind"] - sh["pt_offset"]
             assert sh["pts"].shape[0] == sh["hi"] - sh["lo"]
             assert local.size == 0 or (local.min() >= 0 and local.max() < sh["pts"].shape[0])
