@@ -25,7 +25,18 @@ constexpr int DP_THREADS = 256;
 // per camera: 66 upper-triangle entries of U_c = sum Jc^T Jc (row-major a <= b), then g_c (11)
 constexpr int DP_CAM_VALS = 66 + 11;
 
-struct DenseItem {          // one (point, camera) work item, loaded one tile ahead
+// Two-stage prefetch.  The observation index of a (point, camera) item depends on the point's
+// mask and CSR offset, so a one-step prefetch still stalls on that dependent load (ncu round 2,
+// first version: long-scoreboard stalls 3-11 per issued instruction with 2 warps per scheduler).
+// Stage A loads (mask, obs_start) two tiles ahead, stage B turns them into the item's loads one
+// tile ahead, stage C computes: no load is consumed in the iteration that issued it.
+struct DenseIdx {
+  unsigned long long m;
+  uint32_t os;
+  int ok;
+};
+
+struct DenseItem {          // one (point, camera) work item
   double X[3];
   double E[3];              // optional per-point 3-vector (g~_p)
   double2 ob;
@@ -33,33 +44,54 @@ struct DenseItem {          // one (point, camera) work item, loaded one tile ah
   int live;
 };
 
-__device__ __forceinline__ DenseItem dense_load(long long p, long long P, int c, bool worker,
+__device__ __forceinline__ DenseIdx dense_idx(long long p, long long P, bool worker,
+                                              const uint32_t* __restrict__ obs_start,
+                                              const unsigned long long* __restrict__ mask) {
+  DenseIdx d;
+  d.ok = worker && p < P;
+  d.m = 0ull;
+  d.os = 0u;
+  if (d.ok) { d.m = mask[p]; d.os = obs_start[p]; }
+  return d;
+}
+
+__device__ __forceinline__ DenseItem dense_item(const DenseIdx& d, long long p, int c,
                                                 const double* __restrict__ pts,
                                                 const double2* __restrict__ uv,
                                                 const double* __restrict__ wgt,
-                                                const uint32_t* __restrict__ obs_start,
-                                                const unsigned long long* __restrict__ mask,
                                                 const double* __restrict__ extra3 = nullptr) {
   DenseItem it;
   it.E[0] = it.E[1] = it.E[2] = 0.0;
-  it.live = 0;
   it.w = 0.0;
   it.ob = make_double2(0.0, 0.0);
   it.X[0] = it.X[1] = it.X[2] = 0.0;
-  if (worker && p < P) {
-    const unsigned long long m = mask[p];
-    if ((m >> c) & 1ull) {
-      const long long o = (long long)obs_start[p] + __popcll(m & ((1ull << c) - 1ull));
-      it.live = 1;
-      if (uv) it.ob = uv[o];
-      it.w = wgt ? wgt[o] : 1.0;
-      it.X[0] = pts[3 * p];
-      it.X[1] = pts[3 * p + 1];
-      it.X[2] = pts[3 * p + 2];
-      if (extra3) { it.E[0] = extra3[3 * p]; it.E[1] = extra3[3 * p + 1]; it.E[2] = extra3[3 * p + 2]; }
-    }
+  it.live = d.ok && ((d.m >> c) & 1ull);
+  if (it.live) {
+    const long long o = (long long)d.os + __popcll(d.m & ((1ull << c) - 1ull));
+    if (uv) it.ob = uv[o];
+    it.w = wgt ? wgt[o] : 1.0;
+    it.X[0] = pts[3 * p];
+    it.X[1] = pts[3 * p + 1];
+    it.X[2] = pts[3 * p + 2];
+    if (extra3) { it.E[0] = extra3[3 * p]; it.E[1] = extra3[3 * p + 1]; it.E[2] = extra3[3 * p + 2]; }
   }
   return it;
+}
+
+// U (66 upper-triangle entries, row-major a <= b) += Jc^T Jc with the structural zeros of the
+// cx / cy columns (Jc[0][10] = Jc[1][9] = 0, Jc[0][9] = Jc[1][10] = w) written out by hand.
+__device__ __forceinline__ void accumulate_U(double (&acc)[66 + 11], const ObsLin& L, double w) {
+  int idx = 0;
+#pragma unroll
+  for (int a = 0; a < 9; ++a) {
+#pragma unroll
+    for (int b = a; b < 9; ++b, ++idx)
+      acc[idx] = fma(L.Jc[0][a], L.Jc[0][b], fma(L.Jc[1][a], L.Jc[1][b], acc[idx]));
+    acc[idx] = fma(L.Jc[0][a], w, acc[idx]); ++idx;      // (a, cx)
+    acc[idx] = fma(L.Jc[1][a], w, acc[idx]); ++idx;      // (a, cy)
+  }
+  acc[idx] = fma(w, w, acc[idx]); idx += 2;              // (cx, cx); (cx, cy) stays 0
+  acc[idx] = fma(w, w, acc[idx]);                        // (cy, cy)
 }
 
 // ---- linearise: V, g_p per point; U_c, g_c per camera; cost --------------------------------
@@ -95,13 +127,16 @@ k_linearize_dense(const double* __restrict__ tab, const double* __restrict__ pts
   double cost = 0.0;
   const long long ntiles = (P + PB - 1) / PB;
   long long tile = blockIdx.x;
-  DenseItem nxt = dense_load(tile * PB + pl, P, c, worker && tile < ntiles, pts, uv, wgt, obs_start, mask);
+  const long long G = gridDim.x;
+  DenseItem nxt = dense_item(dense_idx(tile * PB + pl, P, worker && tile < ntiles, obs_start, mask),
+                             tile * PB + pl, c, pts, uv, wgt);
+  DenseIdx idx2 = dense_idx((tile + G) * PB + pl, P, worker && tile + G < ntiles, obs_start, mask);
   __syncthreads();
   int buf = 0;
-  for (; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+  for (; tile < ntiles; tile += G, buf ^= 1) {
     const DenseItem cur = nxt;
-    const long long tn = tile + gridDim.x;
-    nxt = dense_load(tn * PB + pl, P, c, worker && tn < ntiles, pts, uv, wgt, obs_start, mask);
+    nxt = dense_item(idx2, (tile + G) * PB + pl, c, pts, uv, wgt);
+    idx2 = dense_idx((tile + 2 * G) * PB + pl, P, worker && tile + 2 * G < ntiles, obs_start, mask);
     double* pv = s_pv + (size_t)buf * DP_THREADS * 9 + t * 9;
     if (cur.live) {
       double T[CAMTAB];
@@ -119,17 +154,11 @@ k_linearize_dense(const double* __restrict__ tab, const double* __restrict__ pts
       pv[6] = fma(L.Jp[0][0], L.ru, L.Jp[1][0] * L.rv);
       pv[7] = fma(L.Jp[0][1], L.ru, L.Jp[1][1] * L.rv);
       pv[8] = fma(L.Jp[0][2], L.ru, L.Jp[1][2] * L.rv);
-      double J0[11], J1[11];
+      accumulate_U(acc, L, cur.w);
 #pragma unroll
-      for (int a = 0; a < 9; ++a) { J0[a] = L.Jc[0][a]; J1[a] = L.Jc[1][a]; }
-      J0[9] = cur.w; J0[10] = 0.0; J1[9] = 0.0; J1[10] = cur.w;
-      int idx = 0;
-#pragma unroll
-      for (int a = 0; a < 11; ++a)
-#pragma unroll
-        for (int b = a; b < 11; ++b, ++idx) acc[idx] = fma(J0[a], J0[b], fma(J1[a], J1[b], acc[idx]));
-#pragma unroll
-      for (int a = 0; a < 11; ++a) acc[66 + a] = fma(J0[a], L.ru, fma(J1[a], L.rv, acc[66 + a]));
+      for (int a = 0; a < 9; ++a) acc[66 + a] = fma(L.Jc[0][a], L.ru, fma(L.Jc[1][a], L.rv, acc[66 + a]));
+      acc[66 + 9] = fma(cur.w, L.ru, acc[66 + 9]);
+      acc[66 + 10] = fma(cur.w, L.rv, acc[66 + 10]);
     } else if (worker) {
 #pragma unroll
       for (int e = 0; e < 9; ++e) pv[e] = 0.0;
@@ -138,8 +167,8 @@ k_linearize_dense(const double* __restrict__ tab, const double* __restrict__ pts
     // per-point sums over the cameras, fixed order; the other threads go on with the next tile
     const long long p0 = tile * PB;
     const int npts = (int)min((long long)PB, P - p0);
-    if (t < npts * 9) {
-      const int q = t / 9, e = t - 9 * q;
+    for (int j = t; j < npts * 9; j += DP_THREADS) {     // (more than one round only below 9 cameras)
+      const int q = j / 9, e = j - 9 * q;
       const double* src = s_pv + (size_t)buf * DP_THREADS * 9 + (size_t)q * C * 9 + e;
       double s = 0.0;
       for (int k = 0; k < C; ++k) s += src[k * 9];
@@ -180,7 +209,7 @@ __global__ void k_dense_cam_unpack(const double* __restrict__ red, int C, double
 }
 
 // ---- residual (fun): cost only ---------------------------------------------------------------
-__global__ void __launch_bounds__(DP_THREADS)
+__global__ void __launch_bounds__(DP_THREADS, 2)
 k_residual_dense(const double* __restrict__ tab, const double* __restrict__ pts,
                  const double2* __restrict__ uv, const double* __restrict__ wgt,
                  const uint32_t* __restrict__ obs_start,
@@ -200,14 +229,14 @@ k_residual_dense(const double* __restrict__ tab, const double* __restrict__ pts,
   double acc = 0.0;
   const long long ntiles = (P + PB - 1) / PB;
   long long tile = blockIdx.x;
-  DenseItem n0 = dense_load(tile * PB + pl, P, c, worker && tile < ntiles, pts, uv, wgt, obs_start, mask);
-  DenseItem n1 = dense_load((tile + gridDim.x) * PB + pl, P, c, worker && tile + gridDim.x < ntiles, pts, uv,
-                            wgt, obs_start, mask);
-  for (; tile < ntiles; tile += gridDim.x) {
-    const DenseItem cur = n0;
-    n0 = n1;
-    const long long tn = tile + 2 * (long long)gridDim.x;
-    n1 = dense_load(tn * PB + pl, P, c, worker && tn < ntiles, pts, uv, wgt, obs_start, mask);
+  const long long G = gridDim.x;
+  DenseItem nxt = dense_item(dense_idx(tile * PB + pl, P, worker && tile < ntiles, obs_start, mask),
+                             tile * PB + pl, c, pts, uv, wgt);
+  DenseIdx idx2 = dense_idx((tile + G) * PB + pl, P, worker && tile + G < ntiles, obs_start, mask);
+  for (; tile < ntiles; tile += G) {
+    const DenseItem cur = nxt;
+    nxt = dense_item(idx2, (tile + G) * PB + pl, c, pts, uv, wgt);
+    idx2 = dense_idx((tile + 2 * G) * PB + pl, P, worker && tile + 2 * G < ntiles, obs_start, mask);
     if (cur.live) {
       double pu, pv;
       project_tab(T, cur.X[0], cur.X[1], cur.X[2], pu, pv);
@@ -220,7 +249,7 @@ k_residual_dense(const double* __restrict__ tab, const double* __restrict__ pts,
 }
 
 // ---- |J g~|^2 ----------------------------------------------------------------------------------
-__global__ void __launch_bounds__(DP_THREADS)
+__global__ void __launch_bounds__(DP_THREADS, 2)
 k_jdot_dense(const double* __restrict__ tab, const double* __restrict__ pts,
              const double* __restrict__ wgt, const uint32_t* __restrict__ obs_start,
              const unsigned long long* __restrict__ mask, const double* __restrict__ gt_c,
@@ -241,12 +270,14 @@ k_jdot_dense(const double* __restrict__ tab, const double* __restrict__ pts,
   double acc = 0.0;
   const long long ntiles = (P + PB - 1) / PB;
   long long tile = blockIdx.x;
-  DenseItem nxt = dense_load(tile * PB + pl, P, c, worker && tile < ntiles, pts, nullptr, wgt, obs_start, mask,
-                             gt_p);
-  for (; tile < ntiles; tile += gridDim.x) {
+  const long long G = gridDim.x;
+  DenseItem nxt = dense_item(dense_idx(tile * PB + pl, P, worker && tile < ntiles, obs_start, mask),
+                             tile * PB + pl, c, pts, nullptr, wgt, gt_p);
+  DenseIdx idx2 = dense_idx((tile + G) * PB + pl, P, worker && tile + G < ntiles, obs_start, mask);
+  for (; tile < ntiles; tile += G) {
     const DenseItem cur = nxt;
-    const long long tn = tile + gridDim.x;
-    nxt = dense_load(tn * PB + pl, P, c, worker && tn < ntiles, pts, nullptr, wgt, obs_start, mask, gt_p);
+    nxt = dense_item(idx2, (tile + G) * PB + pl, c, pts, nullptr, wgt, gt_p);
+    idx2 = dense_idx((tile + 2 * G) * PB + pl, P, worker && tile + 2 * G < ntiles, obs_start, mask);
     if (cur.live) {
       double T[CAMTAB];
 #pragma unroll

@@ -18,6 +18,7 @@
 #include "eval.cuh"
 #include "ingest.cuh"
 #include "linearize.cuh"
+#include "dense_passes.cuh"
 #include "schur.cuh"
 #include "schur_mma.cuh"
 #include "variants.cuh"
@@ -101,6 +102,10 @@ struct lcba_handle {
   double *d_U = nullptr, *d_Upart = nullptr;
   int camn_grid = 0, camn_pb = 0;
   bool use_mma = false;
+  // dense rigs: passes with a fixed camera per thread (dense_passes.cuh)
+  bool use_dense = false;
+  int dp_pb = 0, dp_grid_lin = 0, dp_grid = 0;
+  double *d_dpart = nullptr, *d_dred = nullptr;
   double* d_Yg = nullptr;        // Y of every (point, camera) in ring layout (k_make_Y), or null
   // outputs on demand
   double2* d_rout = nullptr;
@@ -264,6 +269,8 @@ extern "C" int lcba_create(lcba_t** out, int device) {
                                       (const void*)k_schur_mma<3, true>, (const void*)k_schur_mma<4, true>,
                                       (const void*)k_schur_mma<5, true>, (const void*)k_schur_mma<6, true>,
                                       (const void*)k_sq_camonly<true>, (const void*)k_sq_camonly<false>,
+                                      (const void*)k_linearize_dense, (const void*)k_residual_dense,
+                                      (const void*)k_jdot_dense,
                                       (const void*)k_jdot,      (const void*)k_jacobian_blocks};
     for (const void* f : big_smem_kernels) {
       cudaFuncAttributes fa;
@@ -532,6 +539,20 @@ extern "C" int lcba_set_problem_shard(lcba_t* h, int32_t C, int64_t P, int64_t N
       h->use_mma = true;
     }
   }
+  // dense streaming passes: tensor-path rigs without repeated pairs (LCBA_DENSE_PASSES=0 disables)
+  h->use_dense = false;
+  {
+    const char* env = getenv("LCBA_DENSE_PASSES");
+    if (h->use_mma && h->n_pairs == N && !(env && atoi(env) == 0)) {
+      h->use_dense = true;
+      h->dp_pb = DP_THREADS / C;
+      const long long ntiles = (P + h->dp_pb - 1) / h->dp_pb;
+      h->dp_grid_lin = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)h->sm_count));
+      h->dp_grid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)h->sm_count * 2));
+      LCBA_TRY(dev_alloc(h, &h->d_dpart, (size_t)h->dp_grid_lin * C * DP_CAM_VALS));
+      LCBA_TRY(dev_alloc(h, &h->d_dred, (size_t)C * DP_CAM_VALS));
+    }
+  }
   LCBA_TRY(dev_alloc(h, &h->d_Spart, h->plan.part_stride * max_slices));
   h->d_stats = nullptr;
   if (getenv("LCBA_SCHUR_STATS"))
@@ -675,6 +696,13 @@ static int build_tables(lcba_t* h, int which) {
 // sum r^2 of buffer set `which` -> d_red[0] (all-reduced unless `local`); optional residual output
 static int run_residual(lcba_t* h, int which, double2* r_out, bool local = false) {
   const size_t smem = (size_t)h->C * CAMTAB * 8;
+  if (h->use_dense && !r_out) {
+    KL(h, "residual", k_residual_dense<<<h->dp_grid, DP_THREADS, smem, h->stream>>>(
+          h->d_tab[which], h->d_pts[which], h->d_uv, h->d_w, h->d_obs_start, h->d_mask, h->P, h->C, h->dp_pb,
+          h->d_part));
+    KL(h, "reduce", k_reduce_scalars<<<1, 256, 0, h->stream>>>(h->d_part, h->dp_grid, 1, h->d_red, 1));
+    return local ? LCBA_OK : allreduce(h, h->d_red, 1, NCCL_SUM);
+  }
   KL(h, "residual", k_residual<<<h->obs_grid, 256, smem, h->stream>>>(
         h->d_tab[which], h->d_pts[which], h->d_uv, h->d_cam, h->d_pt, h->d_w, h->d_perm, h->N, h->C,
         r_out, h->d_part));
@@ -742,6 +770,19 @@ static int pass_linearize(lcba_t* h, int first) {
   NvtxRange nvtx_("lcba:linearize");
   const int C = h->C, w = h->cur;
   LCBA_TRY(build_tables(h, w));
+  if (h->use_dense) {
+    // one pass: V, g_p per point; g_c, diag(J^T J) AND the camera blocks U_c per camera; cost
+    const size_t smem = dense_lin_smem_doubles(C) * 8;
+    KL(h, "linearize", k_linearize_dense<<<h->dp_grid_lin, DP_THREADS, smem, h->stream>>>(
+          h->d_tab[w], h->d_pts[w], h->d_uv, h->d_w, h->d_obs_start, h->d_mask, h->P, C, h->dp_pb,
+          h->d_Vg, h->d_dpart, h->d_part));
+    KL(h, "reduce", k_reduce_cols<<<nblk(C * DP_CAM_VALS, RC_COLS), RC_COLS * RC_ROWS, 0, h->stream>>>(
+          h->d_dpart, h->dp_grid_lin, C * DP_CAM_VALS, h->d_dred));
+    KL(h, "reduce", k_dense_cam_unpack<<<nblk(C * DP_CAM_VALS, 128), 128, 0, h->stream>>>(
+          h->d_dred, C, h->d_camsum, h->d_U));
+    KL(h, "reduce", k_reduce_scalars<<<1, 256, 0, h->stream>>>(h->d_part, h->dp_grid_lin, 1,
+                                                               h->d_camsum + C * CAMSUM, 1));
+  } else {
   const size_t smem = linearize_smem_doubles(C) * 8;
   KL(h, "linearize", k_linearize<<<h->lin_grid, LIN_THREADS, smem, h->stream>>>(
         h->d_tab[w], h->d_pts[w], h->d_uv, h->d_cam, h->d_pt, h->d_w, h->d_obs_start, h->d_bins,
@@ -750,6 +791,7 @@ static int pass_linearize(lcba_t* h, int first) {
         h->d_campart, h->lin_grid, C * CAMSUM, h->d_camsum));
   KL(h, "reduce", k_reduce_scalars<<<1, 256, 0, h->stream>>>(h->d_part, h->lin_grid, 1,
                                                              h->d_camsum + C * CAMSUM, 1));
+  }
   // per-point scaling does not depend on the camera sums: run it first so that ONE sum
   // all-reduce carries [camera sums | cost | point sums] and one max all-reduce |g|_inf
   double* pp = h->d_camsum + C * CAMSUM + 1;
@@ -768,9 +810,16 @@ static int pass_jdot(lcba_t* h) {
   NvtxRange nvtx_("lcba:jdot");
   const int C = h->C, w = h->cur;
   const size_t smem = ((size_t)C * CAMTAB + (size_t)C * NCP) * 8;
+  if (h->use_dense) {
+    KL(h, "jdot", k_jdot_dense<<<h->dp_grid, DP_THREADS, (size_t)C * CAMTAB * 8, h->stream>>>(
+          h->d_tab[w], h->d_pts[w], h->d_w, h->d_obs_start, h->d_mask, h->d_gt_c, h->d_gt_p, h->P, C,
+          h->dp_pb, h->d_part));
+    KL(h, "reduce", k_reduce_scalars<<<1, 256, 0, h->stream>>>(h->d_part, h->dp_grid, 1, h->d_red, 1));
+  } else {
   KL(h, "jdot", k_jdot<<<h->obs_grid, 256, smem, h->stream>>>(
         h->d_tab[w], h->d_pts[w], h->d_cam, h->d_pt, h->d_w, h->d_gt_c, h->d_gt_p, h->N, C, h->d_part));
   KL(h, "reduce", k_reduce_scalars<<<1, 256, 0, h->stream>>>(h->d_part, h->obs_grid, 1, h->d_red, 1));
+  }
   LCBA_TRY(allreduce(h, h->d_red, 1, NCCL_SUM));
   KL(h, "ctl", k_ctl_reg<<<1, 1, 0, h->stream>>>(h->d_red, h->d_ctl));
   return check_launch(h, "jdot pass");
@@ -787,11 +836,13 @@ static int pass_schur(lcba_t* h, const double* lam_host_or_null) {
   if (h->use_mma) {
     // dense rigs: SYRK on the FP64 tensor path + the camera blocks U from their own pass
     const MmaPlan& mp = h->mplan;
+    if (!h->use_dense) {      // dense passes: U_c already came out of k_linearize_dense
     const size_t smem_u = ((size_t)((C * CAMTAB + 1) & ~1) + (size_t)h->camn_pb * C) * 8;
     KL(h, "cam_normal", k_cam_normal<<<h->camn_grid, 256, smem_u, h->stream>>>(
           h->d_tab[w], h->d_pts[w], h->d_pair_w, h->d_pair_start, h->d_mask, h->P, C, h->camn_pb, h->d_Upart));
     KL(h, "reduce", k_reduce_cols<<<nblk(C * CAMN_VALS, RC_COLS), RC_COLS * RC_ROWS, 0, h->stream>>>(
           h->d_Upart, h->camn_grid, C * CAMN_VALS, h->d_U));
+    }
     const int nt = (NCP * C + 1 + 7) / 8, last = nt - 6 * ((nt + 5) / 6 - 1);
     if (h->d_Yg) {
       const int pbk = MAKEY_THREADS / C, rpk = mp.kinds[0].rp;
