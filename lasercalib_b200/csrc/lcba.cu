@@ -104,6 +104,9 @@ struct lcba_handle {
   bool use_mma = false;
   // dense rigs: passes with a fixed camera per thread (dense_passes.cuh)
   bool use_dense = false;
+  bool use_pt = false;           // point-parallel residual / jdot / backsub (no repeated pairs)
+  int pt_mode = 1;               // LCBA_PT_PASSES: 0 off, 1 on (default), 2 = (camera, point) variants
+  int ptp_grid = 0;
   int dp_pb = 0, dp_grid_lin = 0, dp_grid = 0;
   double *d_dpart = nullptr, *d_dred = nullptr;
   double* d_Yg = nullptr;        // Y of every (point, camera) in ring layout (k_make_Y), or null
@@ -270,7 +273,8 @@ extern "C" int lcba_create(lcba_t** out, int device) {
                                       (const void*)k_schur_mma<5, true>, (const void*)k_schur_mma<6, true>,
                                       (const void*)k_sq_camonly<true>, (const void*)k_sq_camonly<false>,
                                       (const void*)k_linearize_dense, (const void*)k_residual_dense,
-                                      (const void*)k_jdot_dense,
+                                      (const void*)k_jdot_dense, (const void*)k_backsub_dense,
+                                      (const void*)k_residual_pt, (const void*)k_jdot_pt, (const void*)k_backsub_pt,
                                       (const void*)k_jdot,      (const void*)k_jacobian_blocks};
     for (const void* f : big_smem_kernels) {
       cudaFuncAttributes fa;
@@ -553,6 +557,12 @@ extern "C" int lcba_set_problem_shard(lcba_t* h, int32_t C, int64_t P, int64_t N
       LCBA_TRY(dev_alloc(h, &h->d_dred, (size_t)C * DP_CAM_VALS));
     }
   }
+  {
+    const char* env = getenv("LCBA_PT_PASSES");
+    h->pt_mode = env ? atoi(env) : 1;
+    h->use_pt = h->n_pairs == N && h->pt_mode == 1;
+    h->ptp_grid = (int)std::max<long long>(1, std::min<long long>(nblk(P, PT_THREADS), (long long)h->sm_count * 2));
+  }
   LCBA_TRY(dev_alloc(h, &h->d_Spart, h->plan.part_stride * max_slices));
   h->d_stats = nullptr;
   if (getenv("LCBA_SCHUR_STATS"))
@@ -696,7 +706,13 @@ static int build_tables(lcba_t* h, int which) {
 // sum r^2 of buffer set `which` -> d_red[0] (all-reduced unless `local`); optional residual output
 static int run_residual(lcba_t* h, int which, double2* r_out, bool local = false) {
   const size_t smem = (size_t)h->C * CAMTAB * 8;
-  if (h->use_dense && !r_out) {
+  if (h->use_pt && !r_out) {
+    KL(h, "residual", k_residual_pt<<<h->ptp_grid, PT_THREADS, smem, h->stream>>>(
+          h->d_tab[which], h->d_pts[which], h->d_uv, h->d_w, h->d_obs_start, h->d_mask, h->P, h->C, h->d_part));
+    KL(h, "reduce", k_reduce_scalars<<<1, 256, 0, h->stream>>>(h->d_part, h->ptp_grid, 1, h->d_red, 1));
+    return local ? LCBA_OK : allreduce(h, h->d_red, 1, NCCL_SUM);
+  }
+  if (h->use_dense && h->pt_mode == 2 && !r_out) {
     KL(h, "residual", k_residual_dense<<<h->dp_grid, DP_THREADS, smem, h->stream>>>(
           h->d_tab[which], h->d_pts[which], h->d_uv, h->d_w, h->d_obs_start, h->d_mask, h->P, h->C, h->dp_pb,
           h->d_part));
@@ -810,7 +826,11 @@ static int pass_jdot(lcba_t* h) {
   NvtxRange nvtx_("lcba:jdot");
   const int C = h->C, w = h->cur;
   const size_t smem = ((size_t)C * CAMTAB + (size_t)C * NCP) * 8;
-  if (h->use_dense) {
+  if (h->use_pt) {
+    KL(h, "jdot", k_jdot_pt<<<h->ptp_grid, PT_THREADS, smem, h->stream>>>(
+          h->d_tab[w], h->d_pts[w], h->d_w, h->d_obs_start, h->d_mask, h->d_gt_c, h->d_gt_p, h->P, C, h->d_part));
+    KL(h, "reduce", k_reduce_scalars<<<1, 256, 0, h->stream>>>(h->d_part, h->ptp_grid, 1, h->d_red, 1));
+  } else if (h->use_dense && h->pt_mode == 2) {
     KL(h, "jdot", k_jdot_dense<<<h->dp_grid, DP_THREADS, (size_t)C * CAMTAB * 8, h->stream>>>(
           h->d_tab[w], h->d_pts[w], h->d_w, h->d_obs_start, h->d_mask, h->d_gt_c, h->d_gt_p, h->P, C,
           h->dp_pb, h->d_part));
@@ -952,11 +972,25 @@ static int pass_camera_solve(lcba_t* h, double mu) {
 static int pass_backsub(lcba_t* h) {
   NvtxRange nvtx_("lcba:backsub");
   const int C = h->C, w = h->cur;
+  if (h->use_pt) {
+    const size_t smem = ((size_t)C * CAMTAB + 2 * (size_t)C * NCP) * 8;
+    KL(h, "backsub", k_backsub_pt<<<h->ptp_grid, PT_THREADS, smem, h->stream>>>(
+          h->d_tab[w], h->d_pts[w], h->d_w, h->d_obs_start, h->d_mask, h->P, C, h->d_Vg, h->d_Lz, h->d_scl_p,
+          h->d_gt_c, h->d_gt_p, h->d_pc, h->d_gn_p, h->d_part));
+    KL(h, "reduce", k_reduce_scalars<<<BS_K, 256, 0, h->stream>>>(h->d_part, h->ptp_grid, BS_K, h->d_red, BS_K));
+  } else if (h->use_dense && h->pt_mode == 2) {
+    const size_t smem = dense_bs_smem_doubles(C, h->dp_pb) * 8;
+    KL(h, "backsub", k_backsub_dense<<<h->dp_grid, DP_THREADS, smem, h->stream>>>(
+          h->d_tab[w], h->d_pts[w], h->d_w, h->d_obs_start, h->d_mask, h->P, C, h->dp_pb, h->d_Vg, h->d_Lz,
+          h->d_scl_p, h->d_gt_c, h->d_gt_p, h->d_pc, h->d_gn_p, h->d_part));
+    KL(h, "reduce", k_reduce_scalars<<<BS_K, 256, 0, h->stream>>>(h->d_part, h->dp_grid, BS_K, h->d_red, BS_K));
+  } else {
   const size_t smem = ((size_t)C * CAMTAB + 2 * (size_t)C * NCP + 2 * LIN_THREADS * 3) * 8;
   KL(h, "backsub", k_backsub<<<h->lin_grid, LIN_THREADS, smem, h->stream>>>(
         h->d_tab[w], h->d_pts[w], h->d_cam, h->d_pt, h->d_w, h->d_obs_start, h->d_bins, h->nbins, C,
         h->d_Vg, h->d_Lz, h->d_scl_p, h->d_gt_c, h->d_gt_p, h->d_pc, h->d_gn_p, h->d_part));
   KL(h, "reduce", k_reduce_scalars<<<BS_K, 256, 0, h->stream>>>(h->d_part, h->lin_grid, BS_K, h->d_red, BS_K));
+  }
   LCBA_TRY(allreduce(h, h->d_red, BS_K, NCCL_SUM));
   KL(h, "ctl", k_ctl_sub<<<1, 256, 0, h->stream>>>(h->d_red, h->d_g_c, h->d_gt_c, h->d_pc, h->d_scl_c, C,
                                                    h->d_ctl, h->d_fail, h->d_coef, h->shared_intr));
