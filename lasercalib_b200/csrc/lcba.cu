@@ -514,7 +514,12 @@ extern "C" int lcba_set_problem_shard(lcba_t* h, int32_t C, int64_t P, int64_t N
   h->d_mkinds = nullptr; h->d_U = nullptr; h->d_Upart = nullptr; h->d_Yg = nullptr;
   int max_slices = h->plan.nslices;
   {
-    const bool dense = (double)h->n_pairs >= 0.8 * (double)P * C;
+    // Density crossover, measured on ring24 x 1 M (profiles/r02_density_crossover.txt): the DMMA
+    // SYRK costs ~P C^2 whatever the visibility, the DFMA kernel ~sum k_i^2; at 50 % visibility
+    // the tensor path already wins 3.9 + 0.6 ms against 6.8 ms.  LCBA_MMA_DENSITY overrides.
+    const char* de = getenv("LCBA_MMA_DENSITY");
+    const double min_density = de ? atof(de) : 0.25;
+    const bool dense = (double)h->n_pairs >= min_density * (double)P * C;
     const char* env = getenv("LCBA_SCHUR_MMA");
     const bool want = env ? atoi(env) != 0 : (dense && C >= 8);
     if (want && C <= MMA_MAX_CAMERAS) {

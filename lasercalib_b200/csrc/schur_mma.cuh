@@ -37,7 +37,7 @@ namespace lcba {
 constexpr int MMA_CONS_WARPS = 8;     // consumer warps per CTA (two warpgroups)
 constexpr int MMA_PROD_WARPS = 4;     // producer warps (one warpgroup)
 constexpr int MMA_THREADS = 32 * (MMA_CONS_WARPS + MMA_PROD_WARPS);
-constexpr int MMA_MAX_CAMERAS = 32;   // every kind stages all cameras: beyond this the DFMA kernel
+constexpr int MMA_MAX_CAMERAS = 64;   // = LCBA_MAX_CAMERAS (every kind stages all cameras: 4 points per ring stage at 64)
 #define MMA_CONS_REGS "208"
 #define MMA_PROD_REGS "88"
 

@@ -292,7 +292,7 @@ def _first_cameras(pb, C, min_views=3):
                 camera_ind=ci[sel].copy(), point_ind=remap[pi[sel]].copy())
 
 
-@pytest.mark.parametrize("C", [8, 10, 12, 13, 15, 18, 22, 24, 32])
+@pytest.mark.parametrize("C", [8, 10, 12, 13, 15, 18, 22, 24, 32, 40, 48, 64])
 def test_tensor_path_schur_equals_dfma_path(Engine, monkeypatch, C):
     """The two Schur kernels (DMMA tiles, schur_mma.cuh; DFMA duo blocks, schur.cuh) against each
     other and the oracle for every shape of the last tile group (11 C + 1 rows mod 48), with
