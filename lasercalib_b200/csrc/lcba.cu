@@ -21,6 +21,7 @@
 #include "dense_passes.cuh"
 #include "schur.cuh"
 #include "schur_mma.cuh"
+#include "schur_i8.cuh"
 #include "variants.cuh"
 
 using namespace lcba;
@@ -110,6 +111,15 @@ struct lcba_handle {
   int dp_pb = 0, dp_grid_lin = 0, dp_grid = 0;
   double *d_dpart = nullptr, *d_dred = nullptr;
   double* d_Yg = nullptr;        // Y of every (point, camera) in ring layout (k_make_Y), or null
+  // int8 tensor-core Schur path (schur_i8.cuh)
+  bool use_i8 = false;
+  I8Plan i8plan;
+  I8Work* d_i8work = nullptr;
+  I8Tile* d_i8tiles = nullptr;
+  unsigned char* d_i8planes = nullptr;
+  double *d_i8partial = nullptr, *d_i8rmax = nullptr;
+  int* d_i8erow = nullptr;
+  int i8_gx_max = 0, i8_gx_make = 0, i8_groups = 0;
   // outputs on demand
   double2* d_rout = nullptr;
   double *d_Jc = nullptr, *d_Jp = nullptr;
@@ -275,6 +285,7 @@ extern "C" int lcba_create(lcba_t** out, int device) {
                                       (const void*)k_linearize_dense, (const void*)k_residual_dense,
                                       (const void*)k_jdot_dense, (const void*)k_backsub_dense,
                                       (const void*)k_residual_pt, (const void*)k_jdot_pt, (const void*)k_backsub_pt,
+                                      (const void*)k_i8_syrk, (const void*)k_i8_make,
                                       (const void*)k_jdot,      (const void*)k_jacobian_blocks};
     for (const void* f : big_smem_kernels) {
       cudaFuncAttributes fa;
@@ -525,8 +536,28 @@ extern "C" int lcba_set_problem_shard(lcba_t* h, int32_t C, int64_t P, int64_t N
     if (want && C <= MMA_MAX_CAMERAS) {
       // Y precomputed in HBM when it fits comfortably (288 B per (point, camera)); otherwise the
       // producers of k_schur_mma evaluate it in place (and need the camera tables in shared memory)
-      bool pre = false;
+      // int8 tensor-core path (tcgen05): LCBA_SCHUR_I8=1 enables, default off until selected by the caller
       {
+        const char* ie = getenv("LCBA_SCHUR_I8");
+        h->use_i8 = ie && atoi(ie) != 0;
+      }
+      if (h->use_i8) {
+        h->i8plan = make_i8_plan(C, P, h->sm_count);
+        const I8Plan& ip = h->i8plan;
+        h->i8_groups = (C + I8_GROUP_CAMS - 1) / I8_GROUP_CAMS;
+        h->i8_gx_max = (int)std::max<long long>(1, std::min<long long>(ip.nkb, (long long)h->sm_count * 6 / h->i8_groups));
+        h->i8_gx_make = (int)std::max<long long>(1, std::min<long long>(ip.nkb, (long long)h->sm_count * 5 / h->i8_groups));
+        LCBA_TRY(dev_alloc(h, &h->d_i8work, ip.work.size()));
+        LCBA_TRY(dev_alloc(h, &h->d_i8tiles, ip.tiles.size()));
+        LCBA_CUDA(h, cudaMemcpyAsync(h->d_i8work, ip.work.data(), ip.work.size() * sizeof(I8Work), cudaMemcpyHostToDevice, st));
+        LCBA_CUDA(h, cudaMemcpyAsync(h->d_i8tiles, ip.tiles.data(), ip.tiles.size() * sizeof(I8Tile), cudaMemcpyHostToDevice, st));
+        LCBA_TRY(dev_alloc(h, &h->d_i8planes, ip.plane_bytes));
+        LCBA_TRY(dev_alloc(h, &h->d_i8partial, ip.work.size() * 128 * 64));
+        LCBA_TRY(dev_alloc(h, &h->d_i8rmax, (size_t)h->i8_gx_max * ip.NRG * 8));
+        LCBA_TRY(dev_alloc(h, &h->d_i8erow, (size_t)ip.NRG * 8));
+      }
+      bool pre = false;
+      if (!h->use_i8) {
         int rp = C * 12 + 2;
         while (rp % 16 != 4) ++rp;
         const size_t need = (size_t)(P + 1) * 3 * rp * 8;
@@ -869,6 +900,23 @@ static int pass_schur(lcba_t* h, const double* lam_host_or_null) {
           h->d_Upart, h->camn_grid, C * CAMN_VALS, h->d_U));
     }
     const int nt = (NCP * C + 1 + 7) / 8, last = nt - 6 * ((nt + 5) / 6 - 1);
+    if (h->use_i8) {
+      // 5th-generation tensor cores: digit planes of Y, exact int8 x int8 -> int32 SYRK, FP64 recombination
+      const I8Plan& ip = h->i8plan;
+      const int RP = ip.NRG * 8;
+      const size_t smem_rm = ((size_t)I8_GROUP_CAMS * CAMTAB + 192) * 4;
+      KL(h, "i8_rowmax", k_i8_rowmax<<<dim3(h->i8_gx_max, h->i8_groups), 192, smem_rm, h->stream>>>(
+            h->d_tab[w], h->d_pts[w], h->d_pair_w, h->d_pair_start, h->d_mask, h->d_Lz, h->P, C, RP, h->d_i8rmax));
+      KL(h, "i8_rowmax", k_i8_rowexp<<<nblk(RP, 128), 128, 0, h->stream>>>(h->d_i8rmax, h->i8_gx_max, NCP * C + 1, RP, h->d_i8erow));
+      KL(h, "make_Y", k_i8_make<<<dim3(h->i8_gx_make, h->i8_groups), 192, i8_make_smem_bytes(), h->stream>>>(
+            h->d_tab[w], h->d_pts[w], h->d_pair_w, h->d_pair_start, h->d_mask, h->d_Lz, h->P, C, ip.NRG, h->d_i8erow,
+            h->d_i8planes));
+      KL(h, "schur", k_i8_syrk<<<(unsigned)ip.work.size(), I8_THREADS, ip.smem_bytes, h->stream>>>(
+            h->d_i8planes, ip.NRG, h->d_i8work, h->d_i8partial, h->d_fail));
+      KL(h, "schur_reduce", k_i8_gather<<<(unsigned)ip.tiles.size(), 256, 0, h->stream>>>(
+            h->d_i8partial, h->d_i8tiles, C, h->d_i8erow, pl.npairs, h->d_Sred));
+      KL(h, "schur_reduce", k_add_cam_blocks<<<nblk(C * 121, 128), 128, 0, h->stream>>>(h->d_U, C, h->d_Sred));
+    } else {
     if (h->d_Yg) {
       const int pbk = MAKEY_THREADS / C, rpk = mp.kinds[0].rp;
       const size_t smem_y = ((size_t)((C * CAMTAB + 1) & ~1) + (size_t)3 * pbk * rpk) * 8;
@@ -900,6 +948,7 @@ static int pass_schur(lcba_t* h, const double* lam_host_or_null) {
     KL(h, "schur_reduce", k_reduce_cols<<<nblk((long long)pl.part_stride, RC_COLS), RC_COLS * RC_ROWS, 0, h->stream>>>(
           h->d_Spart, mp.nslices, (int)pl.part_stride, h->d_Sred));
     KL(h, "schur_reduce", k_add_cam_blocks<<<nblk(C * 121, 128), 128, 0, h->stream>>>(h->d_U, C, h->d_Sred));
+    }
   } else {
   dim3 grid(pl.nslices, pl.nkinds);
   // sparse rigs skip duo blocks nobody sees; dense rigs run branch-free

@@ -1,0 +1,599 @@
+// Reduced camera system on the 5th-generation tensor cores: the SYRK  - sum_p [Y; z][Y; z]^T  through
+// an error-free integer split ("Ozaki scheme"), tcgen05.mma kind::i8 with int32 accumulators in TMEM.
+// Prototype, measurements and the accuracy model: tools/ozaki_syrk.cu, profiles/r02_ozaki.txt.
+//
+//   y_rk = 2^e_r * sum_{i<6} d_i(r,k) 2^-8(i+1)     d_i: balanced base-256 digits (int8), e_r from max_k |y_rk|
+//   (Y Y^T)_rc = 2^(e_r+e_c) * sum_{i+j<=6} 2^-8(i+j+2) (D_i D_j^T)_rc       D_i D_j^T exact in int32
+// 48 bits per entry relative to the row maximum; the 26 digit products kept include every coherent
+// term (i = j) down to 2^-64: FP64-grade (numpy model on the oracle's Y: 1e-15 of max|S|).
+//
+// Passes (all in this file):
+//   k_i8_rowmax   : max |Y| per matrix row (thread = fixed camera, 11 running maxima in registers)
+//   k_i8_rowexp   : e_r
+//   k_i8_make     : Y in FP64 -> 48-bit integers -> digit planes in HBM, laid out exactly as the UMMA
+//                   shared-memory operand (K-major, no swizzle, 8 x 16-byte core matrices):
+//                   [K block of 64 kappa = 21 points + 1 zero][slice][row group of 8][k-step 2][k half 2][8][16]
+//   k_i8_syrk     : one CTA = one output tile (128 rows x <= 64 columns, the 7 anti-diagonals d = i + j
+//                   side by side in TMEM) x a range of K blocks; warps 0-3 epilogue (TMEM -> FP64 registers
+//                   before an int32 can overflow), warp 4 bulk-copy producer (one cp.async.bulk per lane,
+//                   12 per K block = 2 k-steps), warp 5 MMA issuer (elect.sync, compile-time MMA plan:
+//                   slice i of the rows against slices 0..6-i of the columns in ONE instruction, N <= 256)
+//   k_i8_gather   : per-CTA partials -> the pair-block layout of Sred (fixed order, no atomics)
+#pragma once
+#include <algorithm>
+#include <vector>
+#include "common.cuh"
+#include "schur_mma.cuh"
+
+namespace lcba {
+
+constexpr int I8_NS = 6;                  // digits per entry
+constexpr int I8_DMAX = 6;                // anti-diagonals kept: i + j <= 6
+constexpr int I8_ND = I8_DMAX + 1;
+constexpr int I8_PTS = 21;                // points per K block (63 kappa + 1 zero column)
+constexpr int I8_STAGES = 3;              // ring stages of one K block (72 KB each)
+constexpr int I8_FLUSH = 224;             // K blocks between TMEM flushes: 6 pairs * 64 * 128^2 * 224 < 2^31
+constexpr int I8_THREADS = 192;
+constexpr int I8_RG_BYTES = 512;          // one row group of one slice of one K block
+constexpr int I8_GROUP_CAMS = 8;          // cameras per k_i8_make block: 88 rows = 11 row groups exactly
+constexpr int I8_GROUP_RG = 13;           // row groups of the last group at most: 8 cameras + z + even padding
+constexpr int I8_GROUP_ROWS = I8_GROUP_RG * 8;
+
+struct I8Work {                           // one CTA of k_i8_syrk
+  int m_rg0, m_nrg, n_rg0, n_nrg;         // row groups of the output tile (rows of A / rows of B)
+  int kb0, kb1;                           // K blocks [kb0, kb1)
+  int transposed, tile;                   // tile holds S[c][r]; tile index
+};
+struct I8Tile { int m_rg0, m_nrg, n_rg0, n_nrg, transposed, w0, nw, pad; };
+
+struct I8Plan {
+  int C = 0, R = 0, NRG = 0;
+  long long nkb = 0;
+  std::vector<I8Tile> tiles;
+  std::vector<I8Work> work;
+  size_t plane_bytes = 0, smem_bytes = 0;
+};
+
+inline I8Plan make_i8_plan(int C, long long P, int sm_count) {
+  I8Plan pl;
+  pl.C = C;
+  pl.R = NCP * C + 1;
+  pl.NRG = (pl.R + 7) / 8;
+  pl.NRG += pl.NRG & 1;                                   // MMA N is a multiple of 16
+  pl.nkb = (P + I8_PTS - 1) / I8_PTS;
+  const int NRG = pl.NRG;
+  const int nmt = (NRG + 15) / 16;
+  const int last_m = NRG - 16 * (nmt - 1);
+  const bool fold = nmt > 1 && last_m <= 4;               // a few rows left over: they become COLUMNS
+  const int nfull = fold ? nmt - 1 : nmt;
+  auto add = [&](int m0, int mn, int n0, int nn, int tr) {
+    I8Tile t{m0, mn, n0, nn, tr, 0, 0, 0};
+    pl.tiles.push_back(t);
+  };
+  for (int mt = 0; mt < nfull; ++mt) {
+    const int m0 = 16 * mt, mn = std::min(16, NRG - m0);
+    for (int n0 = 0; n0 < m0 + mn; n0 += 8) add(m0, mn, n0, std::min(8, m0 + mn - n0), 0);
+  }
+  if (fold) {
+    const int c0 = 16 * (nmt - 1);
+    for (int mt = 0; mt < nfull; ++mt) add(16 * mt, 16, c0, last_m, 1);
+    add(c0, last_m, c0, last_m, 0);
+  }
+  // cost of a K block: measured 931 cycles per k-step for 64 columns, 505 for 16 (issue bound)
+  auto cost = [](const I8Tile& t) { return 0.42 + 0.58 * t.n_nrg / 8.0; };
+  double units = 0;
+  for (auto& t : pl.tiles) units += cost(t);
+  for (size_t ti = 0; ti < pl.tiles.size(); ++ti) {
+    I8Tile& t = pl.tiles[ti];
+    long long n = std::max<long long>(1, (long long)(sm_count * cost(t) / units));
+    n = std::min<long long>(n, pl.nkb);
+    t.w0 = (int)pl.work.size();
+    t.nw = (int)n;
+    for (long long q = 0; q < n; ++q) {
+      I8Work w{t.m_rg0, t.m_nrg, t.n_rg0, t.n_nrg, (int)(pl.nkb * q / n), (int)(pl.nkb * (q + 1) / n), t.transposed, (int)ti};
+      pl.work.push_back(w);
+    }
+  }
+  pl.plane_bytes = (size_t)pl.nkb * I8_NS * NRG * I8_RG_BYTES;
+  pl.smem_bytes = (size_t)I8_STAGES * I8_NS * (16 + 8) * I8_RG_BYTES + 1024;
+  return pl;
+}
+
+// ------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t i8_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void i8_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void i8_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void i8_mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a protocol error must end in an error code, never in a hung GPU.
+template <bool BACKOFF>
+__device__ __forceinline__ void i8_mbar_wait(uint32_t bar, uint32_t parity, int* fail) {
+  const long long t0 = clock64();
+  while (true) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) return;
+    if (BACKOFF) __nanosleep(128);      // waiting warps must not compete with the MMA issuer for issue slots
+    if (clock64() - t0 > 6000000000LL) { atomicOr(fail, 4); asm volatile("trap;"); }
+  }
+}
+__device__ __forceinline__ void i8_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void i8_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void i8_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool i8_elect_one() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(p));
+  return p != 0;
+}
+__device__ __forceinline__ void i8_tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                 "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+               : "r"(taddr) : "memory");
+}
+
+// ------------------------------------------------------------------------------ Y of one (point, camera)
+// y[k][a], a < 11: the 11 rows of the camera for kappa = k (same arithmetic as mma_produce)
+__device__ __forceinline__ void i8_item_values(const double* __restrict__ T, const double (&X)[3],
+                                               const double (&li)[9], double w, bool live, double (&y)[3][NCP]) {
+  ObsLin L;
+  obs_linearize<false>(T, X[0], X[1], X[2], 0.0, 0.0, w, L, live);
+  double Q[2][3];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    Q[i][0] = L.Jp[i][0] * li[0];
+    Q[i][1] = fma(L.Jp[i][0], li[1], L.Jp[i][1] * li[2]);
+    Q[i][2] = fma(L.Jp[i][0], li[3], fma(L.Jp[i][1], li[4], L.Jp[i][2] * li[5]));
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+#pragma unroll
+    for (int a = 0; a < 9; ++a) y[k][a] = fma(L.Jc[0][a], Q[0][k], L.Jc[1][a] * Q[1][k]);
+    y[k][9] = w * Q[0][k];
+    y[k][10] = w * Q[1][k];
+  }
+}
+
+// FP32 twin of i8_item_values for the row maxima only (an exponent needs 1e-4, not 1e-16; FP32 runs
+// at twice the FP64 rate with half the registers).  m[a] = max(m[a], max_k |y[k][a]|).
+__device__ __forceinline__ void i8_item_absmax_f32(const float* __restrict__ T, float X, float Y, float Z,
+                                                   const float (&li)[6], float w, float (&m)[NCP]) {
+  const float* R = T + CT_R;
+  const float xc = fmaf(R[0], X, fmaf(R[1], Y, fmaf(R[2], Z, T[3])));
+  const float yc = fmaf(R[3], X, fmaf(R[4], Y, fmaf(R[5], Z, T[4])));
+  const float zc = fmaf(R[6], X, fmaf(R[7], Y, fmaf(R[8], Z, T[5])));
+  const float iz = 1.0f / zc;
+  const float x = xc * iz, y = yc * iz;
+  const float n = x * x + y * y;
+  const float f = T[6], k1 = T[7], k2 = T[8];
+  const float d = 1.0f + n * (k1 + k2 * n);
+  const float dp = k1 + 2.0f * k2 * n;
+  const float wf = w * f;
+  const float e00 = wf * (d + 2.0f * x * x * dp), e01 = wf * (2.0f * x * y * dp), e11 = wf * (d + 2.0f * y * y * dp);
+  float G[2][3] = {{e00 * iz, e01 * iz, -(e00 * x + e01 * y) * iz}, {e01 * iz, e11 * iz, -(e01 * x + e11 * y) * iz}};
+  float Jc[2][9], Jp[2][3];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) Jp[i][j] = fmaf(G[i][0], R[j], fmaf(G[i][1], R[3 + j], G[i][2] * R[6 + j]));
+  const float* Jr = T + CT_JR;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float c0 = Jr[k], c1 = Jr[3 + k], c2 = Jr[6 + k];
+    const float m0 = fmaf(Y, c2, -Z * c1), m1 = fmaf(Z, c0, -X * c2), m2 = fmaf(X, c1, -Y * c0);
+    Jc[0][k] = -fmaf(Jp[0][0], m0, fmaf(Jp[0][1], m1, Jp[0][2] * m2));
+    Jc[1][k] = -fmaf(Jp[1][0], m0, fmaf(Jp[1][1], m1, Jp[1][2] * m2));
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) { Jc[i][3] = G[i][0]; Jc[i][4] = G[i][1]; Jc[i][5] = G[i][2]; }
+  const float wd = w * d, wfn = wf * n, wfn2 = wfn * n;
+  Jc[0][6] = wd * x;   Jc[1][6] = wd * y;
+  Jc[0][7] = wfn * x;  Jc[1][7] = wfn * y;
+  Jc[0][8] = wfn2 * x; Jc[1][8] = wfn2 * y;
+  float Q[2][3];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    Q[i][0] = Jp[i][0] * li[0];
+    Q[i][1] = fmaf(Jp[i][0], li[1], Jp[i][1] * li[2]);
+    Q[i][2] = fmaf(Jp[i][0], li[3], fmaf(Jp[i][1], li[4], Jp[i][2] * li[5]));
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+#pragma unroll
+    for (int a = 0; a < 9; ++a) m[a] = fmaxf(m[a], fabsf(fmaf(Jc[0][a], Q[0][k], Jc[1][a] * Q[1][k])));
+    m[9] = fmaxf(m[9], fabsf(w * Q[0][k]));
+    m[10] = fmaxf(m[10], fabsf(w * Q[1][k]));
+  }
+}
+
+// Work decomposition of k_i8_rowmax / k_i8_make: block = (K block kb, camera group g of 8 cameras);
+// thread t < 21 * gc: point lane q = t / gc, camera g*8 + t % gc.  blockIdx.y = g, blockIdx.x strides kb.
+// rmax_part[blockIdx.x][NRG * 8]
+__global__ void __launch_bounds__(192, 4)
+k_i8_rowmax(const double* __restrict__ tab, const double* __restrict__ pts, const double* __restrict__ wgt,
+            const uint32_t* __restrict__ obs_start, const unsigned long long* __restrict__ mask,
+            const double* __restrict__ Lz, long long P, int C, int RP, double* __restrict__ rmax_part) {
+  extern __shared__ double s_dyn[];
+  float* s_tab = reinterpret_cast<float*>(s_dyn);                 // 8 * CAMTAB floats
+  float* s_red = s_tab + I8_GROUP_CAMS * CAMTAB;                  // 192
+  const int t = threadIdx.x, g = blockIdx.y;
+  const int c0 = g * I8_GROUP_CAMS, gc = min(I8_GROUP_CAMS, C - c0);
+  for (int i = t; i < gc * CAMTAB; i += blockDim.x) s_tab[i] = (float)tab[c0 * CAMTAB + i];
+  __syncthreads();
+  const bool worker = t < I8_PTS * gc;
+  const int q = worker ? t / gc : 0, cl = worker ? t % gc : 0, cam = c0 + cl;
+  const bool zthread = (g == gridDim.y - 1) && t >= 168 && t < 168 + I8_PTS;      // z row: one thread per point lane
+  float mx[NCP], mz = 0.0f;
+#pragma unroll
+  for (int a = 0; a < NCP; ++a) mx[a] = 0.0f;
+  const long long nkb = (P + I8_PTS - 1) / I8_PTS;
+  for (long long kb = blockIdx.x; kb < nkb; kb += gridDim.x) {
+    if (worker) {
+      const long long p = kb * I8_PTS + q;
+      if (p < P) {
+        const unsigned long long m = mask[p];
+        if ((m >> cam) & 1ull) {
+          const float w = wgt ? (float)wgt[(long long)obs_start[p] + __popcll(m & ((1ull << cam) - 1ull))] : 1.0f;
+          float li[6];
+#pragma unroll
+          for (int a = 0; a < 6; ++a) li[a] = (float)Lz[p * 9 + a];
+          i8_item_absmax_f32(s_tab + cl * CAMTAB, (float)pts[3 * p], (float)pts[3 * p + 1], (float)pts[3 * p + 2], li, w, mx);
+        }
+      }
+    }
+    if (zthread) {
+      const long long p = kb * I8_PTS + (t - 168);
+      if (p < P) mz = fmaxf(mz, fmaxf(fabsf((float)Lz[p * 9 + 6]), fmaxf(fabsf((float)Lz[p * 9 + 7]), fabsf((float)Lz[p * 9 + 8]))));
+    }
+  }
+  // block partial: max over the 21 point lanes of each camera (order irrelevant for a maximum)
+  double* out = rmax_part + (size_t)blockIdx.x * RP;
+#pragma unroll
+  for (int a = 0; a < NCP; ++a) {
+    __syncthreads();
+    s_red[t] = worker ? mx[a] : 0.0f;
+    __syncthreads();
+    if (t < gc) {
+      float m = 0.0f;
+      for (int qq = 0; qq < I8_PTS; ++qq) m = fmaxf(m, s_red[qq * gc + t]);
+      out[(c0 + t) * NCP + a] = (double)m;
+    }
+  }
+  if (g == gridDim.y - 1) {
+    __syncthreads();
+    s_red[t] = zthread ? mz : 0.0f;
+    __syncthreads();
+    if (t == 0) {
+      float m = 0.0f;
+      for (int i = 168; i < 168 + I8_PTS; ++i) m = fmaxf(m, s_red[i]);
+      out[NCP * C] = (double)m;
+    }
+  }
+}
+
+// e_row[r]: |y| 2^-e < 0.25 (two bits of headroom: the top digit stays below 65); rows without data: 0
+__global__ void k_i8_rowexp(const double* __restrict__ rmax_part, int nb, int R, int RP, int* __restrict__ e_row) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= RP) return;
+  double m = 0.0;
+  if (r < R) for (int b = 0; b < nb; ++b) m = fmax(m, rmax_part[(size_t)b * RP + r]);
+  int e = 0;
+  if (m > 0.0 && m < 1e300) { frexp(m * 1.001, &e); e += 2; }    // maxima come from an FP32 evaluation: 1e-3 of slack
+  e_row[r] = e;
+}
+
+// 48-bit integer T -> the 6 balanced digits as the bytes of one word: digit i (0 = most significant)
+// is byte (5 - i) of (T + 0x808080808080) ^ 0x808080808080  (adding 128 to every base-256 digit makes
+// them unsigned, so they are the bytes of the sum; ^ 0x80 maps d + 128 back to int8 d).
+__device__ __forceinline__ unsigned long long i8_encode(double v, double scale) {
+  const long long T = __double2ll_rn(v * scale);
+  return (unsigned long long)(T + 0x808080808080LL) ^ 0x808080808080ULL;
+}
+
+constexpr int I8_VAL_LD = 65;             // row stride (64-bit words) of the staging tile: conflict-free both ways
+inline size_t i8_make_smem_bytes() {
+  return (size_t)I8_GROUP_CAMS * CAMTAB * 8 + (size_t)I8_GROUP_ROWS * 8 + (size_t)I8_GROUP_ROWS * I8_VAL_LD * 8;
+}
+
+// planes[((kb * NS + i) * NRG + rg) * 512 + a * 256 + kh * 128 + r8 * 16 + kbyte], kappa_local = 32 a + 16 kh + kbyte.
+// block (kb stride, g).  Phase 1: thread = (point lane, camera) evaluates Y in FP64 and writes the 33
+// encoded integers to the staging tile [row][kappa] (one 64-bit store each).  Phase 2: a warp takes one
+// (row group, k-step, k half): lane = (row r8, kappa quad) reads 4 integers, picks byte 5 - i of each with
+// PRMT and stores one 32-bit word per slice: 128 contiguous bytes per warp and slice, straight to HBM.
+__global__ void __launch_bounds__(192, 3)
+k_i8_make(const double* __restrict__ tab, const double* __restrict__ pts, const double* __restrict__ wgt,
+          const uint32_t* __restrict__ obs_start, const unsigned long long* __restrict__ mask,
+          const double* __restrict__ Lz, long long P, int C, int NRG, const int* __restrict__ e_row,
+          unsigned char* __restrict__ planes) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  double* s_tab = reinterpret_cast<double*>(s_raw);                                        // 8 * CAMTAB
+  double* s_scale = s_tab + I8_GROUP_CAMS * CAMTAB;                                        // I8_GROUP_ROWS: 2^(48 - e_row)
+  unsigned long long* s_val = reinterpret_cast<unsigned long long*>(s_scale + I8_GROUP_ROWS);   // [rows][I8_VAL_LD]
+  const int t = threadIdx.x, g = blockIdx.y, lane = t & 31, wid = t >> 5;
+  const int c0 = g * I8_GROUP_CAMS, gc = min(I8_GROUP_CAMS, C - c0);
+  const int rg0 = 11 * g;                                    // 8 cameras = 88 rows = 11 row groups
+  const int nrgl = (g == (int)gridDim.y - 1) ? NRG - rg0 : 11;
+  for (int i = t; i < gc * CAMTAB; i += blockDim.x) s_tab[i] = tab[c0 * CAMTAB + i];
+  for (int i = t; i < I8_GROUP_ROWS; i += blockDim.x)
+    s_scale[i] = (rg0 * 8 + i < NRG * 8) ? ldexp(1.0, 8 * I8_NS - e_row[rg0 * 8 + i]) : 0.0;
+  for (int i = t; i < I8_GROUP_ROWS * I8_VAL_LD; i += blockDim.x) s_val[i] = 0ull;       // padding rows / column 63 stay 0
+  __syncthreads();
+  const bool worker = t < I8_PTS * gc;
+  const int q = worker ? t / gc : 0, cl = worker ? t % gc : 0, cam = c0 + cl;
+  const bool zthread = (g == (int)gridDim.y - 1) && t >= 168 && t < 168 + I8_PTS;
+  const int zrow = NCP * C - rg0 * 8;                        // local row of z in the last group
+  const long long nkb = (P + I8_PTS - 1) / I8_PTS;
+  for (long long kb = blockIdx.x; kb < nkb; kb += gridDim.x) {
+    // ---- phase 1
+    if (worker) {
+      const long long p = kb * I8_PTS + q;
+      bool live = false;
+      unsigned long long m = 0ull;
+      if (p < P) { m = mask[p]; live = (m >> cam) & 1ull; }
+      unsigned long long* dst = s_val + (size_t)(cl * NCP) * I8_VAL_LD + 3 * q;
+      if (live) {
+        const double w = wgt ? wgt[(long long)obs_start[p] + __popcll(m & ((1ull << cam) - 1ull))] : 1.0;
+        double li[6];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) li[a] = Lz[p * 9 + a];
+        ObsLin L;
+        obs_linearize<false>(s_tab + cl * CAMTAB, pts[3 * p], pts[3 * p + 1], pts[3 * p + 2], 0.0, 0.0, w, L);
+        const double* sc = s_scale + cl * NCP;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          double q0, q1;                                   // column k of Q = Jp L^-T
+          if (k == 0) { q0 = L.Jp[0][0] * li[0]; q1 = L.Jp[1][0] * li[0]; }
+          else if (k == 1) { q0 = fma(L.Jp[0][0], li[1], L.Jp[0][1] * li[2]); q1 = fma(L.Jp[1][0], li[1], L.Jp[1][1] * li[2]); }
+          else { q0 = fma(L.Jp[0][0], li[3], fma(L.Jp[0][1], li[4], L.Jp[0][2] * li[5]));
+                 q1 = fma(L.Jp[1][0], li[3], fma(L.Jp[1][1], li[4], L.Jp[1][2] * li[5])); }
+#pragma unroll
+          for (int a = 0; a < 9; ++a) dst[a * I8_VAL_LD + k] = i8_encode(fma(L.Jc[0][a], q0, L.Jc[1][a] * q1), sc[a]);
+          dst[9 * I8_VAL_LD + k] = i8_encode(w * q0, sc[9]);
+          dst[10 * I8_VAL_LD + k] = i8_encode(w * q1, sc[10]);
+        }
+      } else {
+        // invisible pairs and the ragged tail are exact zeros
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+          for (int a = 0; a < NCP; ++a) dst[a * I8_VAL_LD + k] = 0ull;
+      }
+    }
+    if (zthread) {
+      const int qq = t - 168;
+      const long long p = kb * I8_PTS + qq;
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        s_val[(size_t)zrow * I8_VAL_LD + 3 * qq + k] = p < P ? i8_encode(Lz[p * 9 + 6 + k], s_scale[zrow]) : 0ull;
+    }
+    __syncthreads();
+    // ---- phase 2
+    const int r8 = lane >> 2, quad = lane & 3;
+    for (int task = wid; task < nrgl * 4; task += 6) {
+      const int rgl = task >> 2, a = (task >> 1) & 1, kh = task & 1;
+      const unsigned long long* src = s_val + (size_t)(rgl * 8 + r8) * I8_VAL_LD + a * 32 + kh * 16 + quad * 4;
+      const unsigned long long v0 = src[0], v1 = src[1], v2 = src[2], v3 = src[3];
+      const unsigned l0 = (unsigned)v0, h0 = (unsigned)(v0 >> 32), l1 = (unsigned)v1, h1 = (unsigned)(v1 >> 32);
+      const unsigned l2 = (unsigned)v2, h2 = (unsigned)(v2 >> 32), l3 = (unsigned)v3, h3 = (unsigned)(v3 >> 32);
+      unsigned char* dst = planes + (((size_t)kb * I8_NS) * NRG + rg0 + rgl) * I8_RG_BYTES + a * 256 + kh * 128 + r8 * 16 + quad * 4;
+      const size_t sstride = (size_t)NRG * I8_RG_BYTES;
+      // slices 0, 1 = bytes 5, 4 (high words); slices 2..5 = bytes 3..0 (low words)
+      unsigned w01, w23;
+      w01 = __byte_perm(h0, h1, 0x0051); w23 = __byte_perm(h2, h3, 0x0051);
+      *reinterpret_cast<unsigned*>(dst + 0 * sstride) = __byte_perm(w01, w23, 0x5410);
+      w01 = __byte_perm(h0, h1, 0x0040); w23 = __byte_perm(h2, h3, 0x0040);
+      *reinterpret_cast<unsigned*>(dst + 1 * sstride) = __byte_perm(w01, w23, 0x5410);
+      w01 = __byte_perm(l0, l1, 0x0073); w23 = __byte_perm(l2, l3, 0x0073);
+      *reinterpret_cast<unsigned*>(dst + 2 * sstride) = __byte_perm(w01, w23, 0x5410);
+      w01 = __byte_perm(l0, l1, 0x0062); w23 = __byte_perm(l2, l3, 0x0062);
+      *reinterpret_cast<unsigned*>(dst + 3 * sstride) = __byte_perm(w01, w23, 0x5410);
+      w01 = __byte_perm(l0, l1, 0x0051); w23 = __byte_perm(l2, l3, 0x0051);
+      *reinterpret_cast<unsigned*>(dst + 4 * sstride) = __byte_perm(w01, w23, 0x5410);
+      w01 = __byte_perm(l0, l1, 0x0040); w23 = __byte_perm(l2, l3, 0x0040);
+      *reinterpret_cast<unsigned*>(dst + 5 * sstride) = __byte_perm(w01, w23, 0x5410);
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------ MMA issue plan
+struct I8Op { int i, j, nj, fresh; };
+template <int NCOL, bool FIRST>
+struct I8KstepPlan {
+  I8Op ops[16];
+  int n;
+  constexpr I8KstepPlan() : ops{}, n(0) {
+    for (int i = 0; i < I8_NS && i <= I8_DMAX; ++i) {
+      const int jmax = (I8_NS - 1 < I8_DMAX - i) ? I8_NS - 1 : I8_DMAX - i;
+      int j = 0;
+      while (j <= jmax) {
+        // block d = i + j is initialised (accumulate = 0) by slice 0, except d = NS-1+i, which slice i
+        // is the first to touch (j = NS-1)
+        const bool fresh = FIRST && (i == 0 || j == I8_NS - 1);
+        int j1 = j;
+        while (j1 + 1 <= jmax && (j1 + 2 - j) * NCOL <= 256 && (FIRST && (i == 0 || j1 + 1 == I8_NS - 1)) == fresh) ++j1;
+        ops[n].i = i; ops[n].j = j; ops[n].nj = j1 - j + 1; ops[n].fresh = fresh ? 1 : 0;
+        ++n;
+        j = j1 + 1;
+      }
+    }
+  }
+};
+
+// one k-step (32 kappa): sA / sB = operand bases of this k-step inside the stage
+template <int NCOL, bool FIRST>
+__device__ __forceinline__ void i8_issue_kstep(uint32_t tmem, uint32_t sA, uint32_t sB, uint32_t a_bytes, uint32_t b_bytes) {
+  constexpr I8KstepPlan<NCOL, FIRST> plan{};
+  constexpr uint32_t DESC_HI = ((uint32_t)I8_RG_BYTES >> 4) | (1u << 14);          // SBO = 512 B, descriptor version 1
+  constexpr uint32_t DESC_LO = (128u >> 4) << 16;                                  // LBO = 128 B, no swizzle
+  constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24);   // s32 += s8 x s8, M = 128
+#pragma unroll
+  for (int q = 0; q < plan.n; ++q) {
+    const uint64_t adesc = ((uint64_t)DESC_HI << 32) | (DESC_LO | (((sA + plan.ops[q].i * a_bytes) >> 4) & 0x3FFF));
+    const uint64_t bdesc = ((uint64_t)DESC_HI << 32) | (DESC_LO | (((sB + plan.ops[q].j * b_bytes) >> 4) & 0x3FFF));
+    i8_mma(tmem + (uint32_t)((plan.ops[q].i + plan.ops[q].j) * NCOL), adesc, bdesc,
+           IDESC | ((uint32_t)(plan.ops[q].nj * NCOL >> 3) << 17), plan.ops[q].fresh ? 0u : 1u);
+  }
+}
+template <int NCOL>
+__device__ __forceinline__ void i8_issue_block(bool first, uint32_t tmem, uint32_t sA, uint32_t sB, uint32_t a_bytes, uint32_t b_bytes) {
+  if (first) i8_issue_kstep<NCOL, true>(tmem, sA, sB, a_bytes, b_bytes);
+  else i8_issue_kstep<NCOL, false>(tmem, sA, sB, a_bytes, b_bytes);
+  i8_issue_kstep<NCOL, false>(tmem, sA + 256, sB + 256, a_bytes, b_bytes);          // second k-step of the K block
+}
+
+// partial[cta][128][64] doubles: sum_d 2^-8(d+2) D_d  (row exponents are applied by k_i8_gather)
+__global__ void __launch_bounds__(I8_THREADS, 1)
+k_i8_syrk(const unsigned char* __restrict__ planes, int NRG, const I8Work* __restrict__ work,
+          double* __restrict__ partial, int* __restrict__ fail) {
+  extern __shared__ __align__(1024) uint8_t i8_smem[];
+  __shared__ __align__(8) uint64_t s_bar[2 * I8_STAGES + 2];
+  __shared__ uint32_t s_tmem;
+  const I8Work W = work[blockIdx.x];
+  const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+  const uint32_t a_bytes = (uint32_t)W.m_nrg * I8_RG_BYTES, b_bytes = (uint32_t)W.n_nrg * I8_RG_BYTES;   // per slice
+  constexpr uint32_t A_REGION = (uint32_t)I8_NS * 16 * I8_RG_BYTES;
+  constexpr uint32_t STAGE_BYTES = (uint32_t)I8_NS * (16 + 8) * I8_RG_BYTES;
+  const uint32_t smem0 = i8_smem_u32(i8_smem);
+  const uint32_t bar_full = i8_smem_u32(&s_bar[0]), bar_empty = i8_smem_u32(&s_bar[I8_STAGES]);
+  const uint32_t bar_tfull = i8_smem_u32(&s_bar[2 * I8_STAGES]), bar_tempty = i8_smem_u32(&s_bar[2 * I8_STAGES + 1]);
+  const int ncol = W.n_nrg * 8;
+  if (tid == 0) {
+    for (int s = 0; s < I8_STAGES; ++s) { i8_mbar_init(bar_full + 8 * s, 1); i8_mbar_init(bar_empty + 8 * s, 1); }
+    i8_mbar_init(bar_tfull, 1);
+    i8_mbar_init(bar_tempty, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (wid == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(i8_smem_u32(&s_tmem)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = s_tmem;
+  const int nkb = W.kb1 - W.kb0;
+
+  if (wid == 4) {
+    // ---- producer: one bulk copy per lane, 2 NS per K block
+    const int ci = lane >> 1, cb = lane & 1;                 // slice, operand (0 = rows / A, 1 = columns / B)
+    for (int it = 0; it < nkb; ++it) {
+      const int st = it % I8_STAGES;
+      if (it >= I8_STAGES) i8_mbar_wait<true>(bar_empty + 8 * st, ((it / I8_STAGES) - 1) & 1, fail);
+      if (lane == 0) i8_mbar_expect_tx(bar_full + 8 * st, (uint32_t)I8_NS * (a_bytes + b_bytes));
+      __syncwarp();
+      if (lane < 2 * I8_NS) {
+        const unsigned char* src = planes + (size_t)(W.kb0 + it) * I8_NS * NRG * I8_RG_BYTES;
+        const uint32_t dstA = smem0 + st * STAGE_BYTES, dstB = dstA + A_REGION;
+        if (cb == 0) i8_bulk_g2s(dstA + ci * a_bytes, src + ((size_t)ci * NRG + W.m_rg0) * I8_RG_BYTES, a_bytes, bar_full + 8 * st);
+        else         i8_bulk_g2s(dstB + ci * b_bytes, src + ((size_t)ci * NRG + W.n_rg0) * I8_RG_BYTES, b_bytes, bar_full + 8 * st);
+      }
+    }
+  } else if (wid == 5) {
+    // ---- MMA issuer: the highest warp id of its scheduler; one elected lane
+    if (i8_elect_one()) {
+      int since_flush = 0, nflush = 0;
+      for (int it = 0; it < nkb; ++it) {
+        const int st = it % I8_STAGES;
+        if (since_flush == 0 && nflush > 0) {                // the accumulators are with the epilogue
+          i8_mbar_wait<false>(bar_tempty, (nflush - 1) & 1, fail);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        i8_mbar_wait<false>(bar_full + 8 * st, (it / I8_STAGES) & 1, fail);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sA = smem0 + st * STAGE_BYTES, sB = sA + A_REGION;
+        const bool first = since_flush == 0;
+        if (ncol == 64) i8_issue_block<64>(first, tmem, sA, sB, a_bytes, b_bytes);
+        else if (ncol == 48) i8_issue_block<48>(first, tmem, sA, sB, a_bytes, b_bytes);
+        else if (ncol == 32) i8_issue_block<32>(first, tmem, sA, sB, a_bytes, b_bytes);
+        else i8_issue_block<16>(first, tmem, sA, sB, a_bytes, b_bytes);
+        i8_commit(bar_empty + 8 * st);                       // frees the ring slot when these MMAs retire
+        ++since_flush;
+        if (since_flush == I8_FLUSH || it == nkb - 1) {
+          i8_commit(bar_tfull);
+          since_flush = 0;
+          ++nflush;
+        }
+      }
+    }
+  } else {
+    // ---- epilogue: TMEM -> FP64 registers (thread = TMEM lane = tile row)
+    const int q = wid & 3;
+    const int row = q * 32 + lane;
+    double acc[64];
+#pragma unroll
+    for (int c = 0; c < 64; ++c) acc[c] = 0.0;
+    const int nfl = (nkb + I8_FLUSH - 1) / I8_FLUSH;
+    for (int f = 0; f < nfl; ++f) {
+      i8_mbar_wait<true>(bar_tfull, f & 1, fail);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+      for (int d = 0; d < I8_ND; ++d) {
+        const double sc = ldexp(1.0, -8 * (d + 2));
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(d * ncol);
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          if (16 * h < ncol) {                               // warp-uniform
+            uint32_t v[16];
+            i8_tmem_ld16(taddr + 16 * h, v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int c = 0; c < 16; ++c) acc[16 * h + c] = fma((double)(int)v[c], sc, acc[16 * h + c]);
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      i8_mbar_arrive(bar_tempty);
+    }
+    double* out = partial + ((size_t)blockIdx.x * 128 + row) * 64;
+#pragma unroll
+    for (int c = 0; c < 64; ++c) out[c] = acc[c];
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (wid == 5) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+// One block per tile: sum the partials of its CTAs (fixed order), apply the row exponents and write
+// - Y Y^T into the pair-block layout of the slice partials (same convention as mma_consume: lower
+// pair blocks 11 x 11, same-camera blocks with both triangles, the z row = reduced right-hand side).
+__global__ void __launch_bounds__(256)
+k_i8_gather(const double* __restrict__ partial, const I8Tile* __restrict__ tiles, int C,
+            const int* __restrict__ e_row, int npairs, double* __restrict__ Sred) {
+  const I8Tile T = tiles[blockIdx.x];
+  const int n = NCP * C;
+  const int nr = T.m_nrg * 8, nc = T.n_nrg * 8;
+  for (int idx = threadIdx.x; idx < nr * nc; idx += blockDim.x) {
+    const int tr = idx / nc, tc = idx - tr * nc;
+    int rho = T.m_rg0 * 8 + tr, sig = T.n_rg0 * 8 + tc;
+    if (T.transposed) { const int x = rho; rho = sig; sig = x; }
+    if (rho > n || sig >= n || sig > rho) continue;
+    double s = 0.0;
+    for (int w = 0; w < T.nw; ++w) s += partial[((size_t)(T.w0 + w) * 128 + tr) * 64 + tc];
+    const double v = -ldexp(s, e_row[rho] + e_row[sig]);
+    const int ck = sig / NCP, cb = sig % NCP;
+    if (rho == n) { Sred[(size_t)npairs * 121 + ck * NCP + cb] = v; continue; }
+    const int cj = rho / NCP, ra = rho % NCP;
+    double* blk = Sred + (size_t)(cj * (cj + 1) / 2 + ck) * 121;
+    blk[ra * NCP + cb] = v;
+    if (cj == ck && ra != cb) blk[cb * NCP + ra] = v;
+  }
+}
+
+}  // namespace lcba

@@ -330,6 +330,71 @@ def test_tensor_path_schur_equals_dfma_path(Engine, monkeypatch, C):
     assert np.abs(outs["mma_pre"]["rhs"] - rhs_or).max() <= 1e-10 * np.abs(rhs_or).max()
 
 
+@pytest.mark.parametrize("C", [8, 9, 13, 16, 18, 24, 29, 32, 48, 64])
+def test_int8_tensor_core_schur_equals_fp64_paths(Engine, monkeypatch, C):
+    """The tcgen05 path (schur_i8.cuh: int8 digit planes of Y, exact int32 products in TMEM, FP64
+    recombination) against the DMMA path and the oracle, for camera counts that exercise every
+    tile shape of its plan (partial last row tile, folded 16/32-column tiles, 48-column tiles),
+    with weights and partial visibility.  FP64-grade: 1e-13 between kernels, 1e-11 / 1e-10 vs numpy."""
+    base = make_rig("ring64" if C > 24 else "ring24", 300, seed=6, variant="volume", p_vis=0.9)
+    pb = _first_cameras(base, C)
+    ci, pi = pb["camera_ind"], pb["point_ind"]
+    w = np.random.default_rng(C).uniform(0.5, 2.0, ci.size)
+    outs = {}
+    for name, env in (("dmma", {"LCBA_SCHUR_MMA": "1", "LCBA_SCHUR_I8": "0"}), ("i8", {"LCBA_SCHUR_MMA": "1", "LCBA_SCHUR_I8": "1"})):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        eng = Engine()
+        eng.set_problem(pb["cams0"], pb["pts0"], pb["points_2d"], ci, pi, w)
+        outs[name] = eng.linearize(1e-3)
+        eng.close()
+        for k in env:
+            monkeypatch.delenv(k)
+    a, b = outs["i8"], outs["dmma"]
+    assert np.abs(a["S"] - a["S"].T).max() == 0.0
+    assert np.abs(a["S"] - b["S"]).max() <= 1e-13 * np.abs(b["S"]).max()
+    assert np.abs(a["rhs"] - b["rhs"]).max() <= 1e-12 * np.abs(b["rhs"]).max()
+    d = np.sqrt(np.abs(np.diag(b["S"])))
+    assert (np.abs(a["S"] - b["S"]) / np.outer(d, d)).max() <= 1e-12          # Jacobi-scaled
+    P = pb["pts0"].shape[0]
+    x0 = np.hstack((pb["cams0"].ravel(), pb["pts0"].ravel()))
+    f = O.fun(x0, C, P, ci, pi, pb["points_2d"], w.reshape(-1, 1))
+    _, Jc, Jp = O.jacobian_blocks(pb["cams0"], pb["pts0"], ci, pi, w)
+    U, gc, V, gp, W = O.normal_blocks(f.reshape(-1, 2), Jc, Jp, C, P, ci, pi)
+    sc = np.hstack((np.sqrt(np.einsum("caa->ca", U)).ravel(), np.sqrt(np.einsum("paa->pa", V)).ravel()))
+    S_or, rhs_or, _ = O.reduced_camera_system(U, gc, V, gp, W, ci, pi, 1e-3, sc)
+    assert np.abs(a["S"] - S_or).max() <= 1e-11 * np.abs(S_or).max()
+    assert np.abs(a["rhs"] - rhs_or).max() <= 1e-10 * np.abs(rhs_or).max()
+
+
+def test_int8_tensor_core_schur_at_depth_and_trajectory(Engine, monkeypatch):
+    """ring24 x 20011 dense points (953 K blocks: ring laps, several TMEM flushes per CTA, ragged
+    last block) vs the oracle, then a full trajectory on ring24 x 5000 against oracle.trf_exact."""
+    monkeypatch.setenv("LCBA_SCHUR_I8", "1")
+    pb = make_rig("ring24", 20011, seed=7, variant="volume", p_vis=1.0)
+    S_or, rhs_or, cost_or = _oracle_reduced(pb, 1e-5)
+    eng = Engine()
+    eng.set_problem(pb["cams0"], pb["pts0"], pb["points_2d"], pb["camera_ind"], pb["point_ind"])
+    o = eng.linearize(1e-5)
+    o2 = eng.linearize(1e-5)
+    eng.close()
+    assert np.array_equal(o["S"], o2["S"])                                     # deterministic
+    assert np.abs(o["S"] - S_or).max() <= 1e-11 * np.abs(S_or).max()
+    assert np.abs(o["rhs"] - rhs_or).max() <= 1e-10 * np.abs(rhs_or).max()
+    pb = make_rig("ring24", 5000, seed=11, variant="volume", p_vis=1.0)
+    ora = O.trf_exact(pb["cams0"], pb["pts0"], pb["points_2d"], pb["camera_ind"], pb["point_ind"], ftol=1e-4)
+    eng = Engine()
+    eng.set_problem(pb["cams0"], pb["pts0"], pb["points_2d"], pb["camera_ind"], pb["point_ind"])
+    res, trace = eng.solve(ftol=1e-4)
+    f, _ = eng.residuals()
+    eng.close()
+    assert res.nfev == ora.nfev and res.njev == ora.njev and res.status == ora.status
+    costs_o = [rec["cost"] for rec in ora.trace] + [ora.cost]
+    np.testing.assert_allclose([row["cost"] for row in trace], costs_o, rtol=3e-7)
+    np.testing.assert_allclose(res.cost, ora.cost, rtol=1e-8)
+    assert abs(O.rmse_px(f) - O.rmse_px(ora.fun)) < 1e-6
+
+
 def _oracle_reduced(pb, lam, w=None):
     C, P = pb["n_cams"], pb["n_points"]
     ci, pi = pb["camera_ind"], pb["point_ind"]
