@@ -536,10 +536,14 @@ extern "C" int lcba_set_problem_shard(lcba_t* h, int32_t C, int64_t P, int64_t N
     if (want && C <= MMA_MAX_CAMERAS) {
       // Y precomputed in HBM when it fits comfortably (288 B per (point, camera)); otherwise the
       // producers of k_schur_mma evaluate it in place (and need the camera tables in shared memory)
-      // int8 tensor-core path (tcgen05): LCBA_SCHUR_I8=1 enables, default off until selected by the caller
+      // int8 tensor-core path (tcgen05, schur_i8.cuh): default for shards of >= 32768 points.  Its
+      // quantisation errors are independent per entry, so its accuracy IMPROVES with the number of
+      // points (2^-46 (rowmax/rms)^2 / sqrt(3 P): 2e-16 at 1 M points, FP64 rounding of the DMMA path
+      // grows like sqrt(3 P)); below ~30 k points the DMMA path is the more accurate one and the
+      // fixed costs of the 148-CTA pipeline do not pay.  LCBA_SCHUR_I8=0/1 overrides.
       {
         const char* ie = getenv("LCBA_SCHUR_I8");
-        h->use_i8 = ie && atoi(ie) != 0;
+        h->use_i8 = ie ? atoi(ie) != 0 : P >= 32768;
       }
       if (h->use_i8) {
         h->i8plan = make_i8_plan(C, P, h->sm_count);
