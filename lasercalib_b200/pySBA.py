@@ -111,6 +111,7 @@ class PySBA:
         self._owner_token = None
         self._fresh_problem = True
         self.last_trace = None
+        self.last_timing = None
         # engine knob (not in the reference): True = the observation arrays are promised not to
         # change, so their device copy is reused between calls; default = re-read every call
         self.observations_static = False
@@ -252,6 +253,8 @@ class PySBA:
             # x0 of the reference: the mean (f, k1, k2) for every camera (pySBA.py:300)
             cams0 = cams0.copy()
             cams0[:, 6:9] = np.mean(cams0[:, 6:9], axis=0)
+        import time as _time
+        t_in0 = _time.perf_counter()
         rank, ws, _ = _dist.world()
         shard = None
         if ws > 1:
@@ -287,6 +290,7 @@ class PySBA:
                                        self.points2D, self._pointWeights)
             if not self._fresh_problem or _shared:   # observations already resident: new x0 only
                 eng.set_params(cams0, pts0)
+        t_in1 = _time.perf_counter()
         live = None
         if verbose == 2:
             # scipy prints the table while it iterates (least_squares(verbose=2), pySBA.py:141)
@@ -302,6 +306,7 @@ class PySBA:
                 raise ValueError("Residuals are not finite in the initial point.") from e
             raise
         self.last_trace = trace
+        t_sol = _time.perf_counter()
         x_direct = None
         nc = numCameras * N_CAM_PARAMS
         if not _fix_cameras and not _shared:
@@ -347,6 +352,9 @@ class PySBA:
             e = engine_at_result()
             return e.grad() if e.generation == gen else e.linearize(1.0)["grad"]
 
+        # wall-clock split of this call: ingest (H2D + validate/sort/narrow/CSR + plans), solve, results D2H
+        self.last_timing = dict(ingest_ms=(t_in1 - t_in0) * 1e3, solve_wall_ms=(t_sol - t_in1) * 1e3,
+                                solve_device_ms=float(res.solve_ms), d2h_ms=(_time.perf_counter() - t_sol) * 1e3)
         if _fix_cameras:
             return self._finish_nocam(lazy_fun, lazy_grad, res, pts, shard, verbose)
         if _shared:
