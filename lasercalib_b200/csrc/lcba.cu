@@ -549,8 +549,8 @@ extern "C" int lcba_set_problem_shard(lcba_t* h, int32_t C, int64_t P, int64_t N
         h->i8plan = make_i8_plan(C, P, h->sm_count);
         const I8Plan& ip = h->i8plan;
         h->i8_groups = (C + I8_GROUP_CAMS - 1) / I8_GROUP_CAMS;
-        h->i8_gx_max = (int)std::max<long long>(1, std::min<long long>(ip.nkb, (long long)h->sm_count * 6 / h->i8_groups));
-        h->i8_gx_make = (int)std::max<long long>(1, std::min<long long>(ip.nkb, (long long)h->sm_count * 5 / h->i8_groups));
+        h->i8_gx_max = (int)std::max<long long>(1, std::min<long long>(ip.nkb, (long long)h->sm_count * 4 / h->i8_groups));   // one wave: 4 blocks per SM
+        h->i8_gx_make = (int)std::max<long long>(1, std::min<long long>(ip.nkb, (long long)h->sm_count * 3 / h->i8_groups));   // one wave: 3 blocks per SM
         LCBA_TRY(dev_alloc(h, &h->d_i8work, ip.work.size()));
         LCBA_TRY(dev_alloc(h, &h->d_i8tiles, ip.tiles.size()));
         LCBA_CUDA(h, cudaMemcpyAsync(h->d_i8work, ip.work.data(), ip.work.size() * sizeof(I8Work), cudaMemcpyHostToDevice, st));
@@ -917,7 +917,7 @@ static int pass_schur(lcba_t* h, const double* lam_host_or_null) {
             h->d_i8planes));
       KL(h, "schur", k_i8_syrk<<<(unsigned)ip.work.size(), I8_THREADS, ip.smem_bytes, h->stream>>>(
             h->d_i8planes, ip.NRG, h->d_i8work, h->d_i8partial, h->d_fail));
-      KL(h, "schur_reduce", k_i8_gather<<<(unsigned)ip.tiles.size(), 256, 0, h->stream>>>(
+      KL(h, "schur_reduce", k_i8_gather<<<dim3((unsigned)ip.tiles.size(), 16), 256, 0, h->stream>>>(
             h->d_i8partial, h->d_i8tiles, C, h->d_i8erow, pl.npairs, h->d_Sred));
       KL(h, "schur_reduce", k_add_cam_blocks<<<nblk(C * 121, 128), 128, 0, h->stream>>>(h->d_U, C, h->d_Sred));
     } else {

@@ -339,21 +339,39 @@ k_i8_make(const double* __restrict__ tab, const double* __restrict__ pts, const 
   const bool zthread = (g == (int)gridDim.y - 1) && t >= 168 && t < 168 + I8_PTS;
   const int zrow = NCP * C - rg0 * 8;                        // local row of z in the last group
   const long long nkb = (P + I8_PTS - 1) / I8_PTS;
+  // inputs of the next K block are loaded before the current one is evaluated (first version: 3 blocks
+  // of 6 warps per SM stalled on the mask -> point -> factor loads: long-scoreboard 3 per issue)
+  unsigned long long n_m = 0ull;
+  double n_X[3] = {0, 0, 0}, n_li[6] = {0, 0, 0, 0, 0, 0};
+  auto prefetch = [&](long long kb) {
+    n_m = 0ull;
+    const long long p = kb * I8_PTS + q;
+    if (worker && kb < nkb && p < P) {
+      n_m = mask[p];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) n_X[a] = pts[3 * p + a];
+#pragma unroll
+      for (int a = 0; a < 6; ++a) n_li[a] = Lz[p * 9 + a];
+    }
+  };
+  prefetch(blockIdx.x);
   for (long long kb = blockIdx.x; kb < nkb; kb += gridDim.x) {
     // ---- phase 1
     if (worker) {
       const long long p = kb * I8_PTS + q;
-      bool live = false;
-      unsigned long long m = 0ull;
-      if (p < P) { m = mask[p]; live = (m >> cam) & 1ull; }
+      const unsigned long long m = n_m;
+      const bool live = (m >> cam) & 1ull;
+      double X[3], li[6];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) X[a] = n_X[a];
+#pragma unroll
+      for (int a = 0; a < 6; ++a) li[a] = n_li[a];
+      prefetch(kb + gridDim.x);
       unsigned long long* dst = s_val + (size_t)(cl * NCP) * I8_VAL_LD + 3 * q;
       if (live) {
         const double w = wgt ? wgt[(long long)obs_start[p] + __popcll(m & ((1ull << cam) - 1ull))] : 1.0;
-        double li[6];
-#pragma unroll
-        for (int a = 0; a < 6; ++a) li[a] = Lz[p * 9 + a];
         ObsLin L;
-        obs_linearize<false>(s_tab + cl * CAMTAB, pts[3 * p], pts[3 * p + 1], pts[3 * p + 2], 0.0, 0.0, w, L);
+        obs_linearize<false>(s_tab + cl * CAMTAB, X[0], X[1], X[2], 0.0, 0.0, w, L);
         const double* sc = s_scale + cl * NCP;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -383,30 +401,33 @@ k_i8_make(const double* __restrict__ tab, const double* __restrict__ pts, const 
         s_val[(size_t)zrow * I8_VAL_LD + 3 * qq + k] = p < P ? i8_encode(Lz[p * 9 + 6 + k], s_scale[zrow]) : 0ull;
     }
     __syncthreads();
-    // ---- phase 2
-    const int r8 = lane >> 2, quad = lane & 3;
-    for (int task = wid; task < nrgl * 4; task += 6) {
-      const int rgl = task >> 2, a = (task >> 1) & 1, kh = task & 1;
-      const unsigned long long* src = s_val + (size_t)(rgl * 8 + r8) * I8_VAL_LD + a * 32 + kh * 16 + quad * 4;
-      const unsigned long long v0 = src[0], v1 = src[1], v2 = src[2], v3 = src[3];
-      const unsigned l0 = (unsigned)v0, h0 = (unsigned)(v0 >> 32), l1 = (unsigned)v1, h1 = (unsigned)(v1 >> 32);
-      const unsigned l2 = (unsigned)v2, h2 = (unsigned)(v2 >> 32), l3 = (unsigned)v3, h3 = (unsigned)(v3 >> 32);
-      unsigned char* dst = planes + (((size_t)kb * I8_NS) * NRG + rg0 + rgl) * I8_RG_BYTES + a * 256 + kh * 128 + r8 * 16 + quad * 4;
+    // ---- phase 2: warp = (row group, k-step), lane = (k half, row r8, 8-kappa half): 8 integers -> one
+    // 8-byte store per slice (a warp writes 2 x 128 contiguous bytes per slice)
+    {
+      const int kh = lane >> 4, r8 = (lane >> 1) & 7, hf = lane & 1;
       const size_t sstride = (size_t)NRG * I8_RG_BYTES;
-      // slices 0, 1 = bytes 5, 4 (high words); slices 2..5 = bytes 3..0 (low words)
-      unsigned w01, w23;
-      w01 = __byte_perm(h0, h1, 0x0051); w23 = __byte_perm(h2, h3, 0x0051);
-      *reinterpret_cast<unsigned*>(dst + 0 * sstride) = __byte_perm(w01, w23, 0x5410);
-      w01 = __byte_perm(h0, h1, 0x0040); w23 = __byte_perm(h2, h3, 0x0040);
-      *reinterpret_cast<unsigned*>(dst + 1 * sstride) = __byte_perm(w01, w23, 0x5410);
-      w01 = __byte_perm(l0, l1, 0x0073); w23 = __byte_perm(l2, l3, 0x0073);
-      *reinterpret_cast<unsigned*>(dst + 2 * sstride) = __byte_perm(w01, w23, 0x5410);
-      w01 = __byte_perm(l0, l1, 0x0062); w23 = __byte_perm(l2, l3, 0x0062);
-      *reinterpret_cast<unsigned*>(dst + 3 * sstride) = __byte_perm(w01, w23, 0x5410);
-      w01 = __byte_perm(l0, l1, 0x0051); w23 = __byte_perm(l2, l3, 0x0051);
-      *reinterpret_cast<unsigned*>(dst + 4 * sstride) = __byte_perm(w01, w23, 0x5410);
-      w01 = __byte_perm(l0, l1, 0x0040); w23 = __byte_perm(l2, l3, 0x0040);
-      *reinterpret_cast<unsigned*>(dst + 5 * sstride) = __byte_perm(w01, w23, 0x5410);
+      unsigned char* lane_dst = planes + (((size_t)kb * I8_NS) * NRG + rg0) * I8_RG_BYTES + kh * 128 + r8 * 16 + hf * 8;
+      const unsigned long long* lane_src = s_val + (size_t)r8 * I8_VAL_LD + kh * 16 + hf * 8;
+      for (int task = wid; task < nrgl * 2; task += 6) {
+        const int rgl = task >> 1, a = task & 1;
+        const unsigned long long* src = lane_src + (size_t)rgl * 8 * I8_VAL_LD + a * 32;
+        unsigned lo[8], hi[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { const unsigned long long v = src[e]; lo[e] = (unsigned)v; hi[e] = (unsigned)(v >> 32); }
+        unsigned char* dst = lane_dst + (size_t)rgl * I8_RG_BYTES + a * 256;
+        // slices 0, 1 = bytes 5, 4 (bytes 1, 0 of the high words); slices 2..5 = bytes 3..0 of the low words
+#pragma unroll
+        for (int i = 0; i < I8_NS; ++i) {
+          const unsigned sel = i == 0 ? 0x0051u : i == 1 ? 0x0040u : i == 2 ? 0x0073u : i == 3 ? 0x0062u : i == 4 ? 0x0051u : 0x0040u;
+          unsigned w[2];
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const unsigned* x = (i < 2) ? hi + 4 * h2 : lo + 4 * h2;
+            w[h2] = __byte_perm(__byte_perm(x[0], x[1], sel), __byte_perm(x[2], x[3], sel), 0x5410);
+          }
+          *reinterpret_cast<uint2*>(dst + (size_t)i * sstride) = make_uint2(w[0], w[1]);
+        }
+      }
     }
     __syncthreads();
   }
@@ -570,7 +591,7 @@ k_i8_syrk(const unsigned char* __restrict__ planes, int NRG, const I8Work* __res
   if (wid == 5) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
-// One block per tile: sum the partials of its CTAs (fixed order), apply the row exponents and write
+// gridDim.x = tiles, gridDim.y splits a tile's entries: sum the partials of its CTAs (fixed order), apply the row exponents and write
 // - Y Y^T into the pair-block layout of the slice partials (same convention as mma_consume: lower
 // pair blocks 11 x 11, same-camera blocks with both triangles, the z row = reduced right-hand side).
 __global__ void __launch_bounds__(256)
@@ -579,7 +600,7 @@ k_i8_gather(const double* __restrict__ partial, const I8Tile* __restrict__ tiles
   const I8Tile T = tiles[blockIdx.x];
   const int n = NCP * C;
   const int nr = T.m_nrg * 8, nc = T.n_nrg * 8;
-  for (int idx = threadIdx.x; idx < nr * nc; idx += blockDim.x) {
+  for (int idx = threadIdx.x + blockDim.x * blockIdx.y; idx < nr * nc; idx += blockDim.x * gridDim.y) {
     const int tr = idx / nc, tc = idx - tr * nc;
     int rho = T.m_rg0 * 8 + tr, sig = T.n_rg0 * 8 + tc;
     if (T.transposed) { const int x = rho; rho = sig; sig = x; }
