@@ -18,7 +18,9 @@ METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.
            "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
            "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__inst_executed.sum",
-           "sm__throughput.avg.pct_of_peak_sustained_elapsed"]
+           "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+           "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+           "lts__t_sector_hit_rate.pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed"]
 SCALE = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
 
 
