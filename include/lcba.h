@@ -243,6 +243,14 @@ int lcba_debug_schur_stats(lcba_t* h, long long* out, int max_ctas, int* nkinds,
 int lcba_debug_mma_plan(int32_t C, int32_t sm_count, int32_t* units_out, int32_t max_kinds,
                         int32_t* nslices_out, int32_t* ok_out);
 
+/* Host-only: the tile / CTA plan of the int8 tensor-core Schur kernel (schur_i8.cuh) for C cameras and P
+ * points.  tiles_out: per tile (first row group of the rows, row groups, first row group of the columns,
+ * row groups, transposed, first CTA, CTAs); work_out: per CTA (tile, first K block, end K block).
+ * Returns the number of tiles (needs no GPU). */
+int lcba_debug_i8_plan(int32_t C, int64_t P, int32_t sm_count, int32_t* tiles_out, int32_t max_tiles,
+                       int32_t* work_out, int32_t max_work, int32_t* nwork_out, int32_t* nrg_out,
+                       int64_t* nkb_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1433,6 +1433,29 @@ extern "C" int lcba_debug_mma_plan(int32_t C, int32_t sm_count, int32_t* units_o
   return pl.nkinds;
 }
 
+// host-only test hook: the tile / CTA plan of the int8 tensor-core Schur kernel (schur_i8.cuh).
+// tiles_out: per tile 7 ints (m_rg0, m_nrg, n_rg0, n_nrg, transposed, first CTA, CTAs); work_out: per CTA
+// 3 ints (tile, kb0, kb1).  Returns the number of tiles; *nwork_out CTAs, *nrg_out row groups, *nkb_out K blocks.
+extern "C" int lcba_debug_i8_plan(int32_t C, int64_t P, int32_t sm_count, int32_t* tiles_out, int32_t max_tiles,
+                                  int32_t* work_out, int32_t max_work, int32_t* nwork_out, int32_t* nrg_out,
+                                  int64_t* nkb_out) {
+  if (C < 1 || C > LCBA_MAX_CAMERAS || P < 1 || !tiles_out) return LCBA_E_ARG;
+  const I8Plan pl = make_i8_plan(C, P, sm_count);
+  for (size_t i = 0; i < pl.tiles.size() && (int)i < max_tiles; ++i) {
+    const I8Tile& t = pl.tiles[i];
+    int32_t* o = tiles_out + 7 * i;
+    o[0] = t.m_rg0; o[1] = t.m_nrg; o[2] = t.n_rg0; o[3] = t.n_nrg; o[4] = t.transposed; o[5] = t.w0; o[6] = t.nw;
+  }
+  if (work_out)
+    for (size_t i = 0; i < pl.work.size() && (int)i < max_work; ++i) {
+      work_out[3 * i] = pl.work[i].tile; work_out[3 * i + 1] = pl.work[i].kb0; work_out[3 * i + 2] = pl.work[i].kb1;
+    }
+  if (nwork_out) *nwork_out = (int32_t)pl.work.size();
+  if (nrg_out) *nrg_out = pl.NRG;
+  if (nkb_out) *nkb_out = pl.nkb;
+  return (int)pl.tiles.size();
+}
+
 // ---- squared-residual variants (pySBA.py:151-206): cost, J^T f, J^T J in one pass ----------
 extern "C" int lcba_sq_normal(lcba_t* h, int32_t mode, const double* theta, double* cost_out,
                               double* g_out, double* H_out) {

@@ -132,3 +132,49 @@ def test_tensor_path_unit_plan_covers_every_tile_once():
         low = np.tril(np.ones((nt, nt), dtype=int))
         np.testing.assert_array_equal(cover, low)
         assert worst <= (1.10 if cams == 24 else 1.40), (cams, worst)
+
+
+def test_int8_schur_plan_covers_the_lower_triangle_once():
+    """Host logic of the int8 tensor-core Schur kernel (schur_i8.cuh make_i8_plan, no GPU): for every
+    camera count the tiles cover each lower-triangle entry of the (11 C + 1)-row matrix exactly once
+    (what k_i8_gather keeps of a tile: transposed tiles swap, entries above the diagonal are dropped),
+    tile widths are multiples of 16 columns and at most 64, row tiles at most 128 rows, the K-block ranges
+    of a tile's CTAs partition [0, nkb), the grid fits one wave, and bench.py's executed-op count agrees
+    with the plan."""
+    import ctypes as C
+    import importlib.util
+    import os
+    from lasercalib_b200 import _cabi
+    lib = _cabi.load()
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for cams in list(range(8, 33)) + [40, 48, 56, 64]:
+        for P in (1000, 125_000, 1_000_000):
+            tiles = np.zeros((128, 7), dtype=np.int32)
+            work = np.zeros((512, 3), dtype=np.int32)
+            nwork, nrg, nkb = C.c_int32(), C.c_int32(), C.c_int64()
+            nt = lib.lcba_debug_i8_plan(cams, P, 148, tiles.ctypes.data_as(C.c_void_p), 128, work.ctypes.data_as(C.c_void_p), 512,
+                                        C.byref(nwork), C.byref(nrg), C.byref(nkb))
+            assert 1 <= nt <= 128 and 1 <= nwork.value <= 148
+            R = 11 * cams + 1
+            assert nrg.value * 8 >= R and nrg.value % 2 == 0 and nkb.value == -(-P // 21)
+            cover = np.zeros((R, R), dtype=int)
+            cols = 0
+            for m0, mn, n0, nn, tr, w0, nw in tiles[:nt]:
+                assert 1 <= mn <= 16 and nn in (2, 4, 6, 8) and nw >= 1
+                cols += 8 * nn
+                rows = np.arange(8 * m0, 8 * (m0 + mn))
+                cs = np.arange(8 * n0, 8 * (n0 + nn))
+                rr, cc = np.meshgrid(rows, cs, indexing="ij")
+                if tr:
+                    rr, cc = cc, rr
+                ok = (rr < R) & (cc < R) & (cc <= rr)
+                np.add.at(cover, (rr[ok], cc[ok]), 1)
+                ranges = work[w0:w0 + nw]
+                assert np.all(ranges[:, 0] == np.where((tiles[:nt, 0] == m0) & (tiles[:nt, 2] == n0) & (tiles[:nt, 4] == tr))[0][0])
+                assert ranges[0, 1] == 0 and ranges[-1, 2] == nkb.value and np.all(ranges[1:, 1] == ranges[:-1, 2])
+                assert np.all(ranges[:, 2] >= ranges[:, 1])
+            np.testing.assert_array_equal(cover, np.tril(np.ones((R, R), dtype=int)))
+            alg, exe = bench.i8_ops(cams, P)
+            assert exe == 26 * 2.0 * 128 * cols * nkb.value * 64 and alg <= exe
