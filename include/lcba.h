@@ -101,7 +101,7 @@ typedef struct lcba_result {
   int32_t n_trace;        /* rows valid in lcba_get_trace */
   double solve_ms;        /* device time of the whole loop (CUDA events) */
   int64_t gpu_launches;   /* kernels launched by this call */
-  double reserved[6];
+  double reserved[6];     /* [0] = CUDA-graph replays inside this solve (0 on the first solve of a problem) */
 } lcba_result;
 
 /* Per-kernel device time (profile=1), accumulated over a solve. */

@@ -129,6 +129,14 @@ struct lcba_handle {
   uint32_t* d_pair_start = nullptr;
   double* d_pair_w = nullptr;
   long long n_pairs = 0;
+  // CUDA graphs of the two static launch sequences of an iteration (body: jdot .. trial; lin: commit +
+  // linearise), one per parameter buffer; captured from the SECOND solve on a resident problem on
+  // (a first solve never pays for capture + instantiation; LCBA_GRAPH=0 disables)
+  struct GraphSlot { cudaGraphExec_t exec = nullptr; long long launches = 0; int key = -1; };
+  GraphSlot g_body[2], g_lin[2];
+  bool use_graphs = true;
+  int solves_on_problem = 0;
+  long long graph_replays = 0;
   // trace / profile
   lcba_iteration_cb iter_cb = nullptr;
   void* iter_cb_user = nullptr;
@@ -172,7 +180,18 @@ static int dev_alloc(lcba_t* h, T** p, size_t count) {
   return LCBA_OK;
 }
 
+static void drop_graphs(lcba_t* h) {
+  lcba_handle::GraphSlot* slots[] = {&h->g_body[0], &h->g_body[1], &h->g_lin[0], &h->g_lin[1]};
+  for (auto* sl : slots) {
+    if (sl->exec) cudaGraphExecDestroy(sl->exec);
+    sl->exec = nullptr;
+    sl->key = -1;
+  }
+  h->solves_on_problem = 0;
+}
+
 static void dev_free_all(lcba_t* h) {
+  drop_graphs(h);          // the graphs hold the device pointers
   for (void* p : h->allocs) cudaFreeAsync(p, h->stream);
   h->allocs.clear();
 }
@@ -1092,6 +1111,47 @@ extern "C" int lcba_set_iteration_callback(lcba_t* h, lcba_iteration_cb cb, void
   return LCBA_OK;
 }
 
+// Run a static launch sequence through a CUDA graph (captured on first use, replayed afterwards):
+// at 8 GPUs an iteration is ~35 launches of mostly microsecond kernels and the gaps between them are
+// a tenth of the step.  Any failure to capture or instantiate (e.g. a driver that cannot capture the
+// cooperative Cholesky launch) switches graphs off for the handle and enqueues directly.
+template <class F>
+static int run_graphed(lcba_t* h, lcba_handle::GraphSlot& slot, int key, bool allowed, F&& enqueue) {
+  if (!allowed || !h->use_graphs || h->prof_on) return enqueue();
+  if (slot.exec && slot.key != key) { cudaGraphExecDestroy(slot.exec); slot.exec = nullptr; }
+  if (!slot.exec) {
+    const long long l0 = h->launches;
+    if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      cudaGetLastError();
+      h->use_graphs = false;
+      return enqueue();
+    }
+    const int rc = enqueue();
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+    if (rc == LCBA_OK && e == cudaSuccess && g) e = cudaGraphInstantiate(&slot.exec, g, 0);
+    if (g) cudaGraphDestroy(g);
+    if (rc != LCBA_OK || e != cudaSuccess || !slot.exec) {
+      cudaGetLastError();
+      slot.exec = nullptr;
+      h->use_graphs = false;
+      h->launches = l0;
+      return enqueue();          // nothing was executed during the failed capture
+    }
+    slot.launches = h->launches - l0;
+    slot.key = key;
+    h->launches = l0;
+  }
+  if (cudaGraphLaunch(slot.exec, h->stream) != cudaSuccess) {
+    cudaGetLastError();
+    h->use_graphs = false;
+    return enqueue();
+  }
+  h->launches += slot.launches;
+  h->graph_replays++;
+  return LCBA_OK;
+}
+
 extern "C" int lcba_solve(lcba_t* h, const lcba_options* opt_in, lcba_result* res) {
   if (!h || !h->have_problem) { set_error(h, "lcba_solve: no problem set"); return LCBA_E_STATE; }
   if (!res) { set_error(h, "lcba_solve: res is NULL"); return LCBA_E_ARG; }
@@ -1102,7 +1162,7 @@ extern "C" int lcba_solve(lcba_t* h, const lcba_options* opt_in, lcba_result* re
   h->trace.clear();
   h->prof.clear();
   h->prof_on = opt.profile != 0;
-  const long long launches0 = h->launches;
+  const long long launches0 = h->launches, replays0 = h->graph_replays;
   if (h->comm) {   // total point count over the ranks (max_nfev = 100 n)
     double v = (double)h->P;
     LCBA_CUDA(h, cudaMemcpyAsync(h->d_red, &v, 8, cudaMemcpyHostToDevice, h->stream));
@@ -1113,6 +1173,13 @@ extern "C" int lcba_solve(lcba_t* h, const lcba_options* opt_in, lcba_result* re
   }
   h->fix_cameras = opt.fix_cameras ? 1 : 0;
   h->shared_intr = (opt.shared_intrinsics && !h->fix_cameras) ? 1 : 0;
+  {
+    static const bool env_off = getenv("LCBA_GRAPH") && atoi(getenv("LCBA_GRAPH")) == 0;
+    if (env_off) h->use_graphs = false;
+  }
+  const bool graphs = h->solves_on_problem >= 1;      // second solve on this resident problem onwards
+  h->solves_on_problem++;
+  const int gkey = h->fix_cameras * 2 + h->shared_intr;
   const long long n_cam = h->fix_cameras ? 0 : (h->shared_intr ? 3 + 8LL * h->C : (long long)h->C * NCP);
   const long long n_total = n_cam + 3 * h->P_total;
   const long long max_nfev = opt.max_nfev > 0 ? opt.max_nfev : 100 * n_total;
@@ -1165,16 +1232,31 @@ extern "C" int lcba_solve(lcba_t* h, const lcba_options* opt_in, lcba_result* re
       if (status >= 0 || limits) break;
     }
 
-    LCBA_TRY(pass_jdot(h));
-    if (h->fix_cameras) {
-      // points only: the normal equations are block diagonal, p_p = (V + lam Dp^2)^-1 g_p
-      KL(h, "point_factor", k_point_factor<<<nblk(h->P, 256), 256, 0, h->stream>>>(
-            h->d_Vg, h->d_scl_p, 0.0, h->d_ctl, h->P, h->d_Lz));
-      LCBA_CUDA(h, cudaMemsetAsync(h->d_pc, 0, (size_t)h->C * NCP * 8, h->stream));
-      LCBA_CUDA(h, cudaMemsetAsync(h->d_fail, 0, 2 * sizeof(int), h->stream));
-    } else {
-      LCBA_TRY(pass_schur(h, nullptr));
-    }
+    auto enqueue_front = [&]() -> int {
+      LCBA_TRY(pass_jdot(h));
+      if (h->fix_cameras) {
+        // points only: the normal equations are block diagonal, p_p = (V + lam Dp^2)^-1 g_p
+        KL(h, "point_factor", k_point_factor<<<nblk(h->P, 256), 256, 0, h->stream>>>(
+              h->d_Vg, h->d_scl_p, 0.0, h->d_ctl, h->P, h->d_Lz));
+        LCBA_CUDA(h, cudaMemsetAsync(h->d_pc, 0, (size_t)h->C * NCP * 8, h->stream));
+        LCBA_CUDA(h, cudaMemsetAsync(h->d_fail, 0, 2 * sizeof(int), h->stream));
+      } else {
+        LCBA_TRY(pass_schur(h, nullptr));
+      }
+      return LCBA_OK;
+    };
+    auto enqueue_back = [&](double mu_) -> int {
+      if (!h->fix_cameras) LCBA_TRY(pass_camera_solve(h, mu_));
+      LCBA_TRY(pass_backsub(h));
+      LCBA_TRY(pass_trial(h));
+      return LCBA_OK;
+    };
+    // the whole static part of the iteration (mu = 0) as one graph; Cholesky retries enqueue directly
+    LCBA_TRY(run_graphed(h, h->g_body[h->cur], gkey, graphs, [&]() -> int {
+      LCBA_TRY(enqueue_front());
+      return enqueue_back(0.0);
+    }));
+    bool body_done = true;
     double mu = 0.0;
     bool have_trial = false;
     double prev_actual = actual, prev_step = step_norm;
@@ -1182,9 +1264,8 @@ extern "C" int lcba_solve(lcba_t* h, const lcba_options* opt_in, lcba_result* re
     int term = -1;
     bool gtol_hit = false;
     while (true) {   // Cholesky retry loop (extra camera damping on breakdown)
-      if (!h->fix_cameras) LCBA_TRY(pass_camera_solve(h, mu));
-      LCBA_TRY(pass_backsub(h));
-      LCBA_TRY(pass_trial(h));
+      if (!body_done) LCBA_TRY(enqueue_back(mu));
+      body_done = false;
       LCBA_TRY(read_ctl(h));
       if (lin_pending) {
         absorb_lin();
@@ -1231,8 +1312,10 @@ extern "C" int lcba_solve(lcba_t* h, const lcba_options* opt_in, lcba_result* re
     if (term >= 0) status = term;
     if (actual > 0.0) {
       h->cur = 1 - h->cur;      // x <- x_new (buffers swap, tables included)
-      KL(h, "ctl", k_ctl_commit<<<1, 1, 0, h->stream>>>(h->d_ctl));
-      LCBA_TRY(pass_linearize(h, 0));
+      LCBA_TRY(run_graphed(h, h->g_lin[h->cur], gkey, graphs, [&]() -> int {
+        KL(h, "ctl", k_ctl_commit<<<1, 1, 0, h->stream>>>(h->d_ctl));
+        return pass_linearize(h, 0);
+      }));
       njev++;
       lin_pending = true;
     } else {
@@ -1255,6 +1338,7 @@ extern "C" int lcba_solve(lcba_t* h, const lcba_options* opt_in, lcba_result* re
   res->n_trace = (int)h->trace.size();
   res->solve_ms = ms;
   res->gpu_launches = h->launches - launches0;
+  res->reserved[0] = (double)(h->graph_replays - replays0);   // CUDA-graph replays inside this solve
   h->prof_on = false;
   return LCBA_OK;
 }

@@ -860,6 +860,33 @@ def test_point_without_observations_is_left_alone(Engine):
     eng.close()
 
 
+def test_repeated_solves_replay_cuda_graphs_bit_identically(Engine):
+    """From the second solve on a resident problem the static launch sequences of an iteration run
+    as CUDA graphs (lcba.cu run_graphed).  Direct launches and graph replays must give bit-identical
+    trajectories, also after switching the solver mode (the graphs are keyed on it) and back."""
+    for rig, npts, pvis in (("ring8", 1500, 0.9), ("example18", 800, 0.6)):
+        pb = make_rig(rig, npts, seed=13, variant="volume", p_vis=pvis)
+        eng = Engine()
+        eng.set_problem(pb["cams0"], pb["pts0"], pb["points_2d"], pb["camera_ind"], pb["point_ind"])
+        runs = []
+        for i in range(4):
+            eng.set_params(pb["cams0"], pb["pts0"])
+            if i == 2:                                       # another mode in between: points only
+                r_nc, _ = eng.solve(ftol=1e-6, fix_cameras=True)
+                assert r_nc.status > 0
+                eng.set_params(pb["cams0"], pb["pts0"])
+            res, trace = eng.solve(ftol=1e-4)
+            cams, pts = eng.get_params()
+            runs.append((res.nfev, res.njev, res.status, res.cost, [t["cost"] for t in trace], cams.copy(), pts.copy(),
+                         int(res.gpu_launches)))
+        for r in runs[1:]:
+            assert r[:3] == runs[0][:3] and r[3] == runs[0][3] and r[4] == runs[0][4]
+            np.testing.assert_array_equal(r[5], runs[0][5])
+            np.testing.assert_array_equal(r[6], runs[0][6])
+            assert r[7] == runs[0][7]                        # the launch count is the same claim either way
+        eng.close()
+
+
 # ------------------------------------------------------------------ full-size properties
 def test_full_size_properties(Engine):
     """Config-3 scale (24 cameras, 1 M points) through size-independent
