@@ -127,9 +127,11 @@ def i8_ops(C, P):
     cols = 0
     for mt in range(nfull):
         m0, mn = 16 * mt, min(16, nrg - 16 * mt)
-        cols += 8 * (m0 + mn)                      # all column tiles of this row tile
+        cols += 8 * (m0 + mn)                      # all column tiles of this row tile (block 1)
+        if fold:
+            cols += 8 * last_m                     # + the folded left-over rows as column block 2
     if fold:
-        cols += 8 * last_m * (nfull + 1)
+        cols += 8 * last_m                         # corner tile
     kpad = -(-P // 21) * 64
     return alg, 26 * 2.0 * 128 * cols * kpad
 

@@ -244,8 +244,9 @@ int lcba_debug_mma_plan(int32_t C, int32_t sm_count, int32_t* units_out, int32_t
                         int32_t* nslices_out, int32_t* ok_out);
 
 /* Host-only: the tile / CTA plan of the int8 tensor-core Schur kernel (schur_i8.cuh) for C cameras and P
- * points.  tiles_out: per tile (first row group of the rows, row groups, first row group of the columns,
- * row groups, transposed, first CTA, CTAs); work_out: per CTA (tile, first K block, end K block).
+ * points.  tiles_out: per tile 8 ints (first row group of the rows, row groups; column block 1: first row
+ * group, row groups; column block 2 (the folded left-over rows, transposed): first row group, row groups;
+ * first CTA, CTAs); work_out: per CTA (index, first K block, end K block).
  * Returns the number of tiles (needs no GPU). */
 int lcba_debug_i8_plan(int32_t C, int64_t P, int32_t sm_count, int32_t* tiles_out, int32_t max_tiles,
                        int32_t* work_out, int32_t max_work, int32_t* nwork_out, int32_t* nrg_out,

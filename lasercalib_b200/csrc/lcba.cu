@@ -1518,7 +1518,7 @@ extern "C" int lcba_debug_mma_plan(int32_t C, int32_t sm_count, int32_t* units_o
 }
 
 // host-only test hook: the tile / CTA plan of the int8 tensor-core Schur kernel (schur_i8.cuh).
-// tiles_out: per tile 7 ints (m_rg0, m_nrg, n_rg0, n_nrg, transposed, first CTA, CTAs); work_out: per CTA
+// tiles_out: per tile 8 ints (m_rg0, m_nrg, n_rg0, n_nrg, n2_rg0, n2_nrg, first CTA, CTAs); work_out: per CTA
 // 3 ints (tile, kb0, kb1).  Returns the number of tiles; *nwork_out CTAs, *nrg_out row groups, *nkb_out K blocks.
 extern "C" int lcba_debug_i8_plan(int32_t C, int64_t P, int32_t sm_count, int32_t* tiles_out, int32_t max_tiles,
                                   int32_t* work_out, int32_t max_work, int32_t* nwork_out, int32_t* nrg_out,
@@ -1527,12 +1527,12 @@ extern "C" int lcba_debug_i8_plan(int32_t C, int64_t P, int32_t sm_count, int32_
   const I8Plan pl = make_i8_plan(C, P, sm_count);
   for (size_t i = 0; i < pl.tiles.size() && (int)i < max_tiles; ++i) {
     const I8Tile& t = pl.tiles[i];
-    int32_t* o = tiles_out + 7 * i;
-    o[0] = t.m_rg0; o[1] = t.m_nrg; o[2] = t.n_rg0; o[3] = t.n_nrg; o[4] = t.transposed; o[5] = t.w0; o[6] = t.nw;
+    int32_t* o = tiles_out + 8 * i;
+    o[0] = t.m_rg0; o[1] = t.m_nrg; o[2] = t.n_rg0; o[3] = t.n_nrg; o[4] = t.n2_rg0; o[5] = t.n2_nrg; o[6] = t.w0; o[7] = t.nw;
   }
   if (work_out)
     for (size_t i = 0; i < pl.work.size() && (int)i < max_work; ++i) {
-      work_out[3 * i] = pl.work[i].tile; work_out[3 * i + 1] = pl.work[i].kb0; work_out[3 * i + 2] = pl.work[i].kb1;
+      work_out[3 * i] = (int32_t)i; work_out[3 * i + 1] = pl.work[i].kb0; work_out[3 * i + 2] = pl.work[i].kb1;
     }
   if (nwork_out) *nwork_out = (int32_t)pl.work.size();
   if (nrg_out) *nrg_out = pl.NRG;

@@ -39,12 +39,15 @@ constexpr int I8_GROUP_CAMS = 8;          // cameras per k_i8_make block: 88 row
 constexpr int I8_GROUP_RG = 13;           // row groups of the last group at most: 8 cameras + z + even padding
 constexpr int I8_GROUP_ROWS = I8_GROUP_RG * 8;
 
-struct I8Work {                           // one CTA of k_i8_syrk
-  int m_rg0, m_nrg, n_rg0, n_nrg;         // row groups of the output tile (rows of A / rows of B)
+// One CTA of k_i8_syrk: rows = row groups [m_rg0, m_rg0 + m_nrg) (the A operand, <= 16), columns = block 1
+// [n_rg0, +n_nrg) and, optionally, block 2 [n2_rg0, +n2_nrg): the few rows left over behind the last full
+// 128-row tile, handled as COLUMNS (the tile entry is S[column][row]); n_nrg + n2_nrg <= 8.  In the partial
+// tile [128][64] block 1 occupies columns [0, 8 n_nrg), block 2 the LAST 8 n2_nrg columns.
+struct I8Work {
+  int m_rg0, m_nrg, n_rg0, n_nrg, n2_rg0, n2_nrg;
   int kb0, kb1;                           // K blocks [kb0, kb1)
-  int transposed, tile;                   // tile holds S[c][r]; tile index
 };
-struct I8Tile { int m_rg0, m_nrg, n_rg0, n_nrg, transposed, w0, nw, pad; };
+struct I8Tile { int m_rg0, m_nrg, n_rg0, n_nrg, n2_rg0, n2_nrg, w0, nw; };
 
 struct I8Plan {
   int C = 0, R = 0, NRG = 0;
@@ -54,6 +57,15 @@ struct I8Plan {
   size_t plane_bytes = 0, smem_bytes = 0;
 };
 
+// Tiles.  Row tiles of 16 row groups (128 rows).  When the last row tile would hold <= 4 row groups
+// (24 cameras: 34 = 16 + 16 + 2) those rows are not given a 128-row tile of their own: they ride as column
+// block 2 of ONE tile of every full row tile (the operand rows A are the same, only 1-2 KB of extra B per K
+// block are loaded) plus a small corner tile; the column tiles are then 8 - last row groups wide so that
+// block 1 + block 2 <= 64 columns (7 anti-diagonals x 64 = 448 TMEM columns).  (First version: separate
+// 16-column tiles with their own K ranges streamed K positions nobody else was reading: 40 % of the
+// kernel's DRAM traffic for 11 % of its work, ncu r02.)
+// K ranges: every non-corner tile gets the SAME number of ranges, so that all CTAs of a K range walk the
+// same K blocks at the same time and share their operands in L2.
 inline I8Plan make_i8_plan(int C, long long P, int sm_count) {
   I8Plan pl;
   pl.C = C;
@@ -64,33 +76,38 @@ inline I8Plan make_i8_plan(int C, long long P, int sm_count) {
   const int NRG = pl.NRG;
   const int nmt = (NRG + 15) / 16;
   const int last_m = NRG - 16 * (nmt - 1);
-  const bool fold = nmt > 1 && last_m <= 4;               // a few rows left over: they become COLUMNS
+  const bool fold = nmt > 1 && last_m <= 4;
   const int nfull = fold ? nmt - 1 : nmt;
-  auto add = [&](int m0, int mn, int n0, int nn, int tr) {
-    I8Tile t{m0, mn, n0, nn, tr, 0, 0, 0};
-    pl.tiles.push_back(t);
-  };
+  const int col_w = fold ? 8 - last_m : 8;
+  const int c0 = 16 * (nmt - 1);
   for (int mt = 0; mt < nfull; ++mt) {
     const int m0 = 16 * mt, mn = std::min(16, NRG - m0);
-    for (int n0 = 0; n0 < m0 + mn; n0 += 8) add(m0, mn, n0, std::min(8, m0 + mn - n0), 0);
+    for (int n0 = 0; n0 < m0 + mn; n0 += col_w) {
+      const int nn = std::min(col_w, m0 + mn - n0);
+      const bool last = n0 + col_w >= m0 + mn;
+      I8Tile t{m0, mn, n0, nn, fold && last ? c0 : 0, fold && last ? last_m : 0, 0, 0};
+      pl.tiles.push_back(t);
+    }
   }
+  const int nmain = (int)pl.tiles.size();
+  long long nranges = std::max<long long>(1, sm_count / nmain), ncorner = 0;
   if (fold) {
-    const int c0 = 16 * (nmt - 1);
-    for (int mt = 0; mt < nfull; ++mt) add(16 * mt, 16, c0, last_m, 1);
-    add(c0, last_m, c0, last_m, 0);
+    // the corner tile (left-over rows x left-over rows) has almost no tensor work but pays the fixed
+    // issue cost of every K block (~0.66 of a main tile's): it needs ~0.66 x as many CTAs as a main
+    // tile has K ranges, or it becomes the critical path (first attempt: 4 CTAs -> 7.8 ms)
+    I8Tile t{c0, last_m, c0, last_m, 0, 0, 0, 0};
+    pl.tiles.push_back(t);
+    nranges = std::max<long long>(1, (long long)(sm_count / (nmain + 0.66)));
+    ncorner = std::max<long long>(1, sm_count - nmain * nranges);
   }
-  // cost of a K block: measured 931 cycles per k-step for 64 columns, 505 for 16 (issue bound)
-  auto cost = [](const I8Tile& t) { return 0.42 + 0.58 * t.n_nrg / 8.0; };
-  double units = 0;
-  for (auto& t : pl.tiles) units += cost(t);
+  nranges = std::min<long long>(nranges, pl.nkb);
   for (size_t ti = 0; ti < pl.tiles.size(); ++ti) {
     I8Tile& t = pl.tiles[ti];
-    long long n = std::max<long long>(1, (long long)(sm_count * cost(t) / units));
-    n = std::min<long long>(n, pl.nkb);
+    const long long n = (int)ti < nmain ? nranges : std::min<long long>(ncorner, pl.nkb);
     t.w0 = (int)pl.work.size();
     t.nw = (int)n;
     for (long long q = 0; q < n; ++q) {
-      I8Work w{t.m_rg0, t.m_nrg, t.n_rg0, t.n_nrg, (int)(pl.nkb * q / n), (int)(pl.nkb * (q + 1) / n), t.transposed, (int)ti};
+      I8Work w{t.m_rg0, t.m_nrg, t.n_rg0, t.n_nrg, t.n2_rg0, t.n2_nrg, (int)(pl.nkb * q / n), (int)(pl.nkb * (q + 1) / n)};
       pl.work.push_back(w);
     }
   }
@@ -472,11 +489,22 @@ __device__ __forceinline__ void i8_issue_kstep(uint32_t tmem, uint32_t sA, uint3
            IDESC | ((uint32_t)(plan.ops[q].nj * NCOL >> 3) << 17), plan.ops[q].fresh ? 0u : 1u);
   }
 }
-template <int NCOL>
-__device__ __forceinline__ void i8_issue_block(bool first, uint32_t tmem, uint32_t sA, uint32_t sB, uint32_t a_bytes, uint32_t b_bytes) {
-  if (first) i8_issue_kstep<NCOL, true>(tmem, sA, sB, a_bytes, b_bytes);
-  else i8_issue_kstep<NCOL, false>(tmem, sA, sB, a_bytes, b_bytes);
-  i8_issue_kstep<NCOL, false>(tmem, sA + 256, sB + 256, a_bytes, b_bytes);          // second k-step of the K block
+// one K block = two k-steps; column block 1 (NCOL1 columns per anti-diagonal, TMEM columns [0, 7 NCOL1)) and
+// the optional block 2 (NCOL2, TMEM columns [7 NCOL1, 7 (NCOL1 + NCOL2)), its own B region)
+template <int NCOL1, int NCOL2>
+__device__ __forceinline__ void i8_issue_block(bool first, uint32_t tmem, uint32_t sA, uint32_t sB1, uint32_t sB2,
+                                               uint32_t a_bytes, uint32_t b1_bytes, uint32_t b2_bytes) {
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    const uint32_t o = 256u * ks;
+    if (ks == 0 && first) {
+      i8_issue_kstep<NCOL1, true>(tmem, sA + o, sB1 + o, a_bytes, b1_bytes);
+      if (NCOL2 > 0) i8_issue_kstep<NCOL2 ? NCOL2 : 16, true>(tmem + I8_ND * NCOL1, sA + o, sB2 + o, a_bytes, b2_bytes);
+    } else {
+      i8_issue_kstep<NCOL1, false>(tmem, sA + o, sB1 + o, a_bytes, b1_bytes);
+      if (NCOL2 > 0) i8_issue_kstep<NCOL2 ? NCOL2 : 16, false>(tmem + I8_ND * NCOL1, sA + o, sB2 + o, a_bytes, b2_bytes);
+    }
+  }
 }
 
 // partial[cta][128][64] doubles: sum_d 2^-8(d+2) D_d  (row exponents are applied by k_i8_gather)
@@ -489,12 +517,14 @@ k_i8_syrk(const unsigned char* __restrict__ planes, int NRG, const I8Work* __res
   const I8Work W = work[blockIdx.x];
   const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
   const uint32_t a_bytes = (uint32_t)W.m_nrg * I8_RG_BYTES, b_bytes = (uint32_t)W.n_nrg * I8_RG_BYTES;   // per slice
+  const uint32_t b2_bytes = (uint32_t)W.n2_nrg * I8_RG_BYTES;
+  const uint32_t B2_OFF = (uint32_t)I8_NS * b_bytes;          // block 2's B region follows block 1's
   constexpr uint32_t A_REGION = (uint32_t)I8_NS * 16 * I8_RG_BYTES;
   constexpr uint32_t STAGE_BYTES = (uint32_t)I8_NS * (16 + 8) * I8_RG_BYTES;
   const uint32_t smem0 = i8_smem_u32(i8_smem);
   const uint32_t bar_full = i8_smem_u32(&s_bar[0]), bar_empty = i8_smem_u32(&s_bar[I8_STAGES]);
   const uint32_t bar_tfull = i8_smem_u32(&s_bar[2 * I8_STAGES]), bar_tempty = i8_smem_u32(&s_bar[2 * I8_STAGES + 1]);
-  const int ncol = W.n_nrg * 8;
+  const int ncol = W.n_nrg * 8, ncol2 = W.n2_nrg * 8;
   if (tid == 0) {
     for (int s = 0; s < I8_STAGES; ++s) { i8_mbar_init(bar_full + 8 * s, 1); i8_mbar_init(bar_empty + 8 * s, 1); }
     i8_mbar_init(bar_tfull, 1);
@@ -512,18 +542,20 @@ k_i8_syrk(const unsigned char* __restrict__ planes, int NRG, const I8Work* __res
   const int nkb = W.kb1 - W.kb0;
 
   if (wid == 4) {
-    // ---- producer: one bulk copy per lane, 2 NS per K block
-    const int ci = lane >> 1, cb = lane & 1;                 // slice, operand (0 = rows / A, 1 = columns / B)
+    // ---- producer: one bulk copy per lane: (digit, operand) = A, B of block 1, B of block 2
+    const int ci = lane / 3, cb = lane - 3 * ci;
+    const bool mine = lane < 3 * I8_NS && (cb < 2 || W.n2_nrg > 0);
     for (int it = 0; it < nkb; ++it) {
       const int st = it % I8_STAGES;
       if (it >= I8_STAGES) i8_mbar_wait<true>(bar_empty + 8 * st, ((it / I8_STAGES) - 1) & 1, fail);
-      if (lane == 0) i8_mbar_expect_tx(bar_full + 8 * st, (uint32_t)I8_NS * (a_bytes + b_bytes));
+      if (lane == 0) i8_mbar_expect_tx(bar_full + 8 * st, (uint32_t)I8_NS * (a_bytes + b_bytes + b2_bytes));
       __syncwarp();
-      if (lane < 2 * I8_NS) {
-        const unsigned char* src = planes + (size_t)(W.kb0 + it) * I8_NS * NRG * I8_RG_BYTES;
+      if (mine) {
+        const unsigned char* src = planes + (size_t)(W.kb0 + it) * I8_NS * NRG * I8_RG_BYTES + (size_t)ci * NRG * I8_RG_BYTES;
         const uint32_t dstA = smem0 + st * STAGE_BYTES, dstB = dstA + A_REGION;
-        if (cb == 0) i8_bulk_g2s(dstA + ci * a_bytes, src + ((size_t)ci * NRG + W.m_rg0) * I8_RG_BYTES, a_bytes, bar_full + 8 * st);
-        else         i8_bulk_g2s(dstB + ci * b_bytes, src + ((size_t)ci * NRG + W.n_rg0) * I8_RG_BYTES, b_bytes, bar_full + 8 * st);
+        if (cb == 0) i8_bulk_g2s(dstA + ci * a_bytes, src + (size_t)W.m_rg0 * I8_RG_BYTES, a_bytes, bar_full + 8 * st);
+        else if (cb == 1) i8_bulk_g2s(dstB + ci * b_bytes, src + (size_t)W.n_rg0 * I8_RG_BYTES, b_bytes, bar_full + 8 * st);
+        else i8_bulk_g2s(dstB + B2_OFF + ci * b2_bytes, src + (size_t)W.n2_rg0 * I8_RG_BYTES, b2_bytes, bar_full + 8 * st);
       }
     }
   } else if (wid == 5) {
@@ -540,10 +572,20 @@ k_i8_syrk(const unsigned char* __restrict__ planes, int NRG, const I8Work* __res
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sA = smem0 + st * STAGE_BYTES, sB = sA + A_REGION;
         const bool first = since_flush == 0;
-        if (ncol == 64) i8_issue_block<64>(first, tmem, sA, sB, a_bytes, b_bytes);
-        else if (ncol == 48) i8_issue_block<48>(first, tmem, sA, sB, a_bytes, b_bytes);
-        else if (ncol == 32) i8_issue_block<32>(first, tmem, sA, sB, a_bytes, b_bytes);
-        else i8_issue_block<16>(first, tmem, sA, sB, a_bytes, b_bytes);
+        const uint32_t sB2 = sB + B2_OFF;
+        if (ncol2 == 0) {
+          if (ncol == 64) i8_issue_block<64, 0>(first, tmem, sA, sB, sB2, a_bytes, b_bytes, b2_bytes);
+          else if (ncol == 48) i8_issue_block<48, 0>(first, tmem, sA, sB, sB2, a_bytes, b_bytes, b2_bytes);
+          else if (ncol == 32) i8_issue_block<32, 0>(first, tmem, sA, sB, sB2, a_bytes, b_bytes, b2_bytes);
+          else i8_issue_block<16, 0>(first, tmem, sA, sB, sB2, a_bytes, b_bytes, b2_bytes);
+        } else if (ncol2 == 16) {
+          if (ncol == 48) i8_issue_block<48, 16>(first, tmem, sA, sB, sB2, a_bytes, b_bytes, b2_bytes);
+          else if (ncol == 32) i8_issue_block<32, 16>(first, tmem, sA, sB, sB2, a_bytes, b_bytes, b2_bytes);
+          else i8_issue_block<16, 16>(first, tmem, sA, sB, sB2, a_bytes, b_bytes, b2_bytes);
+        } else {
+          if (ncol == 32) i8_issue_block<32, 32>(first, tmem, sA, sB, sB2, a_bytes, b_bytes, b2_bytes);
+          else i8_issue_block<16, 32>(first, tmem, sA, sB, sB2, a_bytes, b_bytes, b2_bytes);
+        }
         i8_commit(bar_empty + 8 * st);                       // frees the ring slot when these MMAs retire
         ++since_flush;
         if (since_flush == I8_FLUSH || it == nkb - 1) {
@@ -570,9 +612,15 @@ k_i8_syrk(const unsigned char* __restrict__ planes, int NRG, const I8Work* __res
         const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(d * ncol);
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
-          if (16 * h < ncol) {                               // warp-uniform
+          if (16 * h < ncol) {                               // block 1: columns [0, ncol); warp-uniform
             uint32_t v[16];
             i8_tmem_ld16(taddr + 16 * h, v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int c = 0; c < 16; ++c) acc[16 * h + c] = fma((double)(int)v[c], sc, acc[16 * h + c]);
+          } else if (16 * h >= 64 - ncol2) {                 // block 2: the last ncol2 columns of the tile
+            uint32_t v[16];
+            i8_tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(I8_ND * ncol + d * ncol2 + 16 * h - (64 - ncol2)), v);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
             for (int c = 0; c < 16; ++c) acc[16 * h + c] = fma((double)(int)v[c], sc, acc[16 * h + c]);
@@ -591,19 +639,22 @@ k_i8_syrk(const unsigned char* __restrict__ planes, int NRG, const I8Work* __res
   if (wid == 5) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
-// gridDim.x = tiles, gridDim.y splits a tile's entries: sum the partials of its CTAs (fixed order), apply the row exponents and write
-// - Y Y^T into the pair-block layout of the slice partials (same convention as mma_consume: lower
-// pair blocks 11 x 11, same-camera blocks with both triangles, the z row = reduced right-hand side).
+// gridDim.x = tiles, gridDim.y splits a tile's entries: sum the partials of its CTAs (fixed order), apply the row
+// exponents and write - Y Y^T into the pair-block layout of the slice partials (same convention as
+// mma_consume: lower pair blocks 11 x 11, same-camera blocks with both triangles, the z row = reduced
+// right-hand side).  Tile columns [0, 8 n_nrg) = block 1, the last 8 n2_nrg columns = block 2 (transposed).
 __global__ void __launch_bounds__(256)
 k_i8_gather(const double* __restrict__ partial, const I8Tile* __restrict__ tiles, int C,
             const int* __restrict__ e_row, int npairs, double* __restrict__ Sred) {
   const I8Tile T = tiles[blockIdx.x];
   const int n = NCP * C;
-  const int nr = T.m_nrg * 8, nc = T.n_nrg * 8;
+  const int nr = T.m_nrg * 8, nc1 = T.n_nrg * 8, nc2 = T.n2_nrg * 8, nc = nc1 + nc2;
   for (int idx = threadIdx.x + blockDim.x * blockIdx.y; idx < nr * nc; idx += blockDim.x * gridDim.y) {
-    const int tr = idx / nc, tc = idx - tr * nc;
-    int rho = T.m_rg0 * 8 + tr, sig = T.n_rg0 * 8 + tc;
-    if (T.transposed) { const int x = rho; rho = sig; sig = x; }
+    const int tr = idx / nc, tcl = idx - tr * nc;
+    const bool second = tcl >= nc1;
+    const int tc = second ? 64 - nc2 + (tcl - nc1) : tcl;               // column inside the 64-wide partial tile
+    int rho = T.m_rg0 * 8 + tr, sig = second ? T.n2_rg0 * 8 + (tcl - nc1) : T.n_rg0 * 8 + tcl;
+    if (second) { const int x = rho; rho = sig; sig = x; }
     if (rho > n || sig >= n || sig > rho) continue;
     double s = 0.0;
     for (int w = 0; w < T.nw; ++w) s += partial[((size_t)(T.w0 + w) * 128 + tr) * 64 + tc];

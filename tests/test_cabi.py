@@ -137,10 +137,10 @@ def test_tensor_path_unit_plan_covers_every_tile_once():
 def test_int8_schur_plan_covers_the_lower_triangle_once():
     """Host logic of the int8 tensor-core Schur kernel (schur_i8.cuh make_i8_plan, no GPU): for every
     camera count the tiles cover each lower-triangle entry of the (11 C + 1)-row matrix exactly once
-    (what k_i8_gather keeps of a tile: transposed tiles swap, entries above the diagonal are dropped),
-    tile widths are multiples of 16 columns and at most 64, row tiles at most 128 rows, the K-block ranges
-    of a tile's CTAs partition [0, nkb), the grid fits one wave, and bench.py's executed-op count agrees
-    with the plan."""
+    (what k_i8_gather keeps of a tile: block 2 is transposed, entries above the diagonal are dropped),
+    block widths are multiples of 16 columns, both blocks together at most 64 (7 anti-diagonals x 64 TMEM
+    columns), row tiles at most 128 rows, every non-corner tile has the SAME K partition (operand sharing in
+    L2), the ranges partition [0, nkb), the grid fits one wave, and bench.py's executed-op count agrees."""
     import ctypes as C
     import importlib.util
     import os
@@ -151,30 +151,36 @@ def test_int8_schur_plan_covers_the_lower_triangle_once():
     spec.loader.exec_module(bench)
     for cams in list(range(8, 33)) + [40, 48, 56, 64]:
         for P in (1000, 125_000, 1_000_000):
-            tiles = np.zeros((128, 7), dtype=np.int32)
+            tiles = np.zeros((256, 8), dtype=np.int32)
             work = np.zeros((512, 3), dtype=np.int32)
             nwork, nrg, nkb = C.c_int32(), C.c_int32(), C.c_int64()
-            nt = lib.lcba_debug_i8_plan(cams, P, 148, tiles.ctypes.data_as(C.c_void_p), 128, work.ctypes.data_as(C.c_void_p), 512,
+            nt = lib.lcba_debug_i8_plan(cams, P, 148, tiles.ctypes.data_as(C.c_void_p), 256, work.ctypes.data_as(C.c_void_p), 512,
                                         C.byref(nwork), C.byref(nrg), C.byref(nkb))
-            assert 1 <= nt <= 128 and 1 <= nwork.value <= 148
+            assert 1 <= nt <= 256 and 1 <= nwork.value <= 148, (cams, nt, nwork.value)
             R = 11 * cams + 1
             assert nrg.value * 8 >= R and nrg.value % 2 == 0 and nkb.value == -(-P // 21)
             cover = np.zeros((R, R), dtype=int)
             cols = 0
-            for m0, mn, n0, nn, tr, w0, nw in tiles[:nt]:
-                assert 1 <= mn <= 16 and nn in (2, 4, 6, 8) and nw >= 1
-                cols += 8 * nn
+            nws = []
+            for m0, mn, n0, nn, n20, n2n, w0, nw in tiles[:nt]:
+                assert 1 <= mn <= 16 and nn in (2, 4, 6, 8) and n2n in (0, 2, 4) and nn + n2n <= 8 and nw >= 1
+                cols += 8 * (nn + n2n)
+                nws.append(nw)
                 rows = np.arange(8 * m0, 8 * (m0 + mn))
-                cs = np.arange(8 * n0, 8 * (n0 + nn))
-                rr, cc = np.meshgrid(rows, cs, indexing="ij")
-                if tr:
-                    rr, cc = cc, rr
-                ok = (rr < R) & (cc < R) & (cc <= rr)
-                np.add.at(cover, (rr[ok], cc[ok]), 1)
+                for c_lo, c_n, transposed in ((n0, nn, False), (n20, n2n, True)):
+                    if c_n == 0:
+                        continue
+                    cs = np.arange(8 * c_lo, 8 * (c_lo + c_n))
+                    rr, cc = np.meshgrid(rows, cs, indexing="ij")
+                    if transposed:
+                        rr, cc = cc, rr
+                    ok = (rr < R) & (cc < R) & (cc <= rr)
+                    np.add.at(cover, (rr[ok], cc[ok]), 1)
                 ranges = work[w0:w0 + nw]
-                assert np.all(ranges[:, 0] == np.where((tiles[:nt, 0] == m0) & (tiles[:nt, 2] == n0) & (tiles[:nt, 4] == tr))[0][0])
                 assert ranges[0, 1] == 0 and ranges[-1, 2] == nkb.value and np.all(ranges[1:, 1] == ranges[:-1, 2])
                 assert np.all(ranges[:, 2] >= ranges[:, 1])
             np.testing.assert_array_equal(cover, np.tril(np.ones((R, R), dtype=int)))
+            main = nws[:-1] if len(set(nws)) > 1 else nws
+            assert len(set(main)) == 1, (cams, nws)          # one K partition for all non-corner tiles
             alg, exe = bench.i8_ops(cams, P)
             assert exe == 26 * 2.0 * 128 * cols * nkb.value * 64 and alg <= exe
