@@ -113,6 +113,8 @@ struct lcba_handle {
   double* d_Yg = nullptr;        // Y of every (point, camera) in ring layout (k_make_Y), or null
   // int8 tensor-core Schur path (schur_i8.cuh)
   bool use_i8 = false;
+  bool i8_tma = false;           // operand loads through TMA tensor maps (else 1-D bulk copies)
+  I8Maps i8maps;
   I8Plan i8plan;
   I8Work* d_i8work = nullptr;
   I8Tile* d_i8tiles = nullptr;
@@ -304,7 +306,7 @@ extern "C" int lcba_create(lcba_t** out, int device) {
                                       (const void*)k_linearize_dense, (const void*)k_residual_dense,
                                       (const void*)k_jdot_dense, (const void*)k_backsub_dense,
                                       (const void*)k_residual_pt, (const void*)k_jdot_pt, (const void*)k_backsub_pt,
-                                      (const void*)k_i8_syrk, (const void*)k_i8_make,
+                                      (const void*)k_i8_syrk<true>, (const void*)k_i8_syrk<false>, (const void*)k_i8_make,
                                       (const void*)k_jdot,      (const void*)k_jacobian_blocks};
     for (const void* f : big_smem_kernels) {
       cudaFuncAttributes fa;
@@ -575,6 +577,11 @@ extern "C" int lcba_set_problem_shard(lcba_t* h, int32_t C, int64_t P, int64_t N
         LCBA_CUDA(h, cudaMemcpyAsync(h->d_i8work, ip.work.data(), ip.work.size() * sizeof(I8Work), cudaMemcpyHostToDevice, st));
         LCBA_CUDA(h, cudaMemcpyAsync(h->d_i8tiles, ip.tiles.data(), ip.tiles.size() * sizeof(I8Tile), cudaMemcpyHostToDevice, st));
         LCBA_TRY(dev_alloc(h, &h->d_i8planes, ip.plane_bytes));
+        {
+          const char* te = getenv("LCBA_I8_TMA");
+          h->i8_tma = !(te && atoi(te) == 0) && i8_encode_maps(ip, h->d_i8planes, &h->i8maps);
+          if (!h->i8_tma) memset(&h->i8maps, 0, sizeof(h->i8maps));
+        }
         LCBA_TRY(dev_alloc(h, &h->d_i8partial, ip.work.size() * 128 * 64));
         LCBA_TRY(dev_alloc(h, &h->d_i8rmax, (size_t)h->i8_gx_max * ip.NRG * 8));
         LCBA_TRY(dev_alloc(h, &h->d_i8erow, (size_t)ip.NRG * 8));
@@ -934,8 +941,12 @@ static int pass_schur(lcba_t* h, const double* lam_host_or_null) {
       KL(h, "make_Y", k_i8_make<<<dim3(h->i8_gx_make, h->i8_groups), 192, i8_make_smem_bytes(), h->stream>>>(
             h->d_tab[w], h->d_pts[w], h->d_pair_w, h->d_pair_start, h->d_mask, h->d_Lz, h->P, C, ip.NRG, h->d_i8erow,
             h->d_i8planes));
-      KL(h, "schur", k_i8_syrk<<<(unsigned)ip.work.size(), I8_THREADS, ip.smem_bytes, h->stream>>>(
-            h->d_i8planes, ip.NRG, h->d_i8work, h->d_i8partial, h->d_fail));
+      if (h->i8_tma)
+        KL(h, "schur", k_i8_syrk<true><<<(unsigned)ip.work.size(), I8_THREADS, ip.smem_bytes, h->stream>>>(
+              h->i8maps, h->d_i8planes, ip.NRG, h->d_i8work, h->d_i8partial, h->d_fail));
+      else
+        KL(h, "schur", k_i8_syrk<false><<<(unsigned)ip.work.size(), I8_THREADS, ip.smem_bytes, h->stream>>>(
+              h->i8maps, h->d_i8planes, ip.NRG, h->d_i8work, h->d_i8partial, h->d_fail));
       KL(h, "schur_reduce", k_i8_gather<<<dim3((unsigned)ip.tiles.size(), 16), 256, 0, h->stream>>>(
             h->d_i8partial, h->d_i8tiles, C, h->d_i8erow, pl.npairs, h->d_Sred));
       KL(h, "schur_reduce", k_add_cam_blocks<<<nblk(C * 121, 128), 128, 0, h->stream>>>(h->d_U, C, h->d_Sred));

@@ -20,6 +20,7 @@
 //                   slice i of the rows against slices 0..6-i of the columns in ONE instruction, N <= 256)
 //   k_i8_gather   : per-CTA partials -> the pair-block layout of Sred (fixed order, no atomics)
 #pragma once
+#include <cuda.h>
 #include <algorithm>
 #include <vector>
 #include "common.cuh"
@@ -46,12 +47,22 @@ constexpr int I8_GROUP_ROWS = I8_GROUP_RG * 8;
 struct I8Work {
   int m_rg0, m_nrg, n_rg0, n_nrg, n2_rg0, n2_nrg;
   int kb0, kb1;                           // K blocks [kb0, kb1)
+  int map_a, map_b1, map_b2, pad;         // tensor-map index (box height) of the three operand loads
 };
+// TMA tensor maps over the digit planes, one per box height that the plan uses: a 4-D tensor
+// (128 u32 = one 512-byte row group, NRG row groups, 6 digits, K blocks); a box of (128, h, 6, 1) lands
+// in shared memory as [digit][h row groups][512 B] = the UMMA operand of all six digits in ONE instruction
+// (the 1-D bulk-copy version needs one copy per digit and operand: 18 per K block, and the ~110 cycles of
+// issue per copy made the copy engine, not the tensor pipe, set the pace).
+constexpr int I8_MAX_MAPS = 6;
+struct alignas(64) I8Maps { CUtensorMap m[I8_MAX_MAPS]; };
 struct I8Tile { int m_rg0, m_nrg, n_rg0, n_nrg, n2_rg0, n2_nrg, w0, nw; };
 
 struct I8Plan {
   int C = 0, R = 0, NRG = 0;
   long long nkb = 0;
+  int map_heights[I8_MAX_MAPS] = {0, 0, 0, 0, 0, 0};   // box heights (row groups) of the tensor maps
+  int nmaps = 0;                                       // > I8_MAX_MAPS: too many shapes, use 1-D bulk copies
   std::vector<I8Tile> tiles;
   std::vector<I8Work> work;
   size_t plane_bytes = 0, smem_bytes = 0;
@@ -106,8 +117,16 @@ inline I8Plan make_i8_plan(int C, long long P, int sm_count) {
     const long long n = (int)ti < nmain ? nranges : std::min<long long>(ncorner, pl.nkb);
     t.w0 = (int)pl.work.size();
     t.nw = (int)n;
+    auto map_of = [&](int h) {
+      if (h == 0) return 0;
+      for (int i = 0; i < pl.nmaps && i < I8_MAX_MAPS; ++i) if (pl.map_heights[i] == h) return i;
+      if (pl.nmaps < I8_MAX_MAPS) pl.map_heights[pl.nmaps] = h;
+      return pl.nmaps++;
+    };
+    const int ma = map_of(t.m_nrg), mb1 = map_of(t.n_nrg), mb2 = map_of(t.n2_nrg);
     for (long long q = 0; q < n; ++q) {
-      I8Work w{t.m_rg0, t.m_nrg, t.n_rg0, t.n_nrg, t.n2_rg0, t.n2_nrg, (int)(pl.nkb * q / n), (int)(pl.nkb * (q + 1) / n)};
+      I8Work w{t.m_rg0, t.m_nrg, t.n_rg0, t.n_nrg, t.n2_rg0, t.n2_nrg, (int)(pl.nkb * q / n), (int)(pl.nkb * (q + 1) / n),
+               ma, mb1, mb2, 0};
       pl.work.push_back(w);
     }
   }
@@ -116,7 +135,39 @@ inline I8Plan make_i8_plan(int C, long long P, int sm_count) {
   return pl;
 }
 
+// Encode the tensor maps of a plan over `planes` (host).  Returns false when the driver entry point is
+// missing, an encode fails or the plan has more shapes than I8_MAX_MAPS: the caller then uses bulk copies.
+inline bool i8_encode_maps(const I8Plan& pl, void* planes, I8Maps* out) {
+  if (pl.nmaps <= 0 || pl.nmaps > I8_MAX_MAPS) return false;
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+      qres != cudaDriverEntryPointSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  const cuuint64_t gdim[4] = {128, (cuuint64_t)pl.NRG, (cuuint64_t)I8_NS, (cuuint64_t)pl.nkb};
+  const cuuint64_t gstr[3] = {(cuuint64_t)I8_RG_BYTES, (cuuint64_t)pl.NRG * I8_RG_BYTES, (cuuint64_t)I8_NS * pl.NRG * I8_RG_BYTES};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  memset(out, 0, sizeof(*out));
+  for (int i = 0; i < pl.nmaps; ++i) {
+    const cuuint32_t box[4] = {128, (cuuint32_t)pl.map_heights[i], (cuuint32_t)I8_NS, 1};
+    const CUresult r = ((EncodeFn)fn)(&out->m[i], CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, planes, gdim, gstr, box, estr,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return false;
+  }
+  return true;
+}
+
 // ------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ void i8_tma_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+               ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
+}
 __device__ __forceinline__ uint32_t i8_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void i8_mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -508,9 +559,10 @@ __device__ __forceinline__ void i8_issue_block(bool first, uint32_t tmem, uint32
 }
 
 // partial[cta][128][64] doubles: sum_d 2^-8(d+2) D_d  (row exponents are applied by k_i8_gather)
+template <bool TMA>
 __global__ void __launch_bounds__(I8_THREADS, 1)
-k_i8_syrk(const unsigned char* __restrict__ planes, int NRG, const I8Work* __restrict__ work,
-          double* __restrict__ partial, int* __restrict__ fail) {
+k_i8_syrk(const __grid_constant__ I8Maps maps, const unsigned char* __restrict__ planes, int NRG,
+          const I8Work* __restrict__ work, double* __restrict__ partial, int* __restrict__ fail) {
   extern __shared__ __align__(1024) uint8_t i8_smem[];
   __shared__ __align__(8) uint64_t s_bar[2 * I8_STAGES + 2];
   __shared__ uint32_t s_tmem;
@@ -542,7 +594,22 @@ k_i8_syrk(const unsigned char* __restrict__ planes, int NRG, const I8Work* __res
   const int nkb = W.kb1 - W.kb0;
 
   if (wid == 4) {
-    // ---- producer: one bulk copy per lane: (digit, operand) = A, B of block 1, B of block 2
+    if (TMA) {
+      // ---- producer, TMA: one tensor copy per operand (all six digits of A / B1 / B2), issued by one lane
+      if (lane == 0) {
+        for (int it = 0; it < nkb; ++it) {
+          const int st = it % I8_STAGES;
+          if (it >= I8_STAGES) i8_mbar_wait<true>(bar_empty + 8 * st, ((it / I8_STAGES) - 1) & 1, fail);
+          i8_mbar_expect_tx(bar_full + 8 * st, (uint32_t)I8_NS * (a_bytes + b_bytes + b2_bytes));
+          const uint32_t dstA = smem0 + st * STAGE_BYTES, dstB = dstA + A_REGION;
+          const int kb = W.kb0 + it;
+          i8_tma_4d(dstA, &maps.m[W.map_a], 0, W.m_rg0, 0, kb, bar_full + 8 * st);
+          i8_tma_4d(dstB, &maps.m[W.map_b1], 0, W.n_rg0, 0, kb, bar_full + 8 * st);
+          if (W.n2_nrg > 0) i8_tma_4d(dstB + B2_OFF, &maps.m[W.map_b2], 0, W.n2_rg0, 0, kb, bar_full + 8 * st);
+        }
+      }
+    } else {
+    // ---- producer, 1-D bulk copies: one per lane: (digit, operand) = A, B of block 1, B of block 2
     const int ci = lane / 3, cb = lane - 3 * ci;
     const bool mine = lane < 3 * I8_NS && (cb < 2 || W.n2_nrg > 0);
     for (int it = 0; it < nkb; ++it) {
@@ -557,6 +624,7 @@ k_i8_syrk(const unsigned char* __restrict__ planes, int NRG, const I8Work* __res
         else if (cb == 1) i8_bulk_g2s(dstB + ci * b_bytes, src + (size_t)W.n_rg0 * I8_RG_BYTES, b_bytes, bar_full + 8 * st);
         else i8_bulk_g2s(dstB + B2_OFF + ci * b2_bytes, src + (size_t)W.n2_rg0 * I8_RG_BYTES, b2_bytes, bar_full + 8 * st);
       }
+    }
     }
   } else if (wid == 5) {
     // ---- MMA issuer: the highest warp id of its scheduler; one elected lane
