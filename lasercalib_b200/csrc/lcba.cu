@@ -632,8 +632,9 @@ extern "C" int lcba_set_problem_shard(lcba_t* h, int32_t C, int64_t P, int64_t N
   LCBA_TRY(dev_alloc(h, &h->d_Spart, h->plan.part_stride * max_slices));
   h->d_stats = nullptr;
   if (getenv("LCBA_SCHUR_STATS"))
-    LCBA_TRY(dev_alloc(h, &h->d_stats, (size_t)std::max(h->plan.nslices * h->plan.nkinds,
-                                                        h->use_mma ? h->mplan.nslices * h->mplan.nkinds : 0) * 4));
+    LCBA_TRY(dev_alloc(h, &h->d_stats, (size_t)std::max(std::max(h->plan.nslices * h->plan.nkinds,
+                                                                 h->use_mma ? h->mplan.nslices * h->mplan.nkinds : 0),
+                                                        256) * 4));
   LCBA_CUDA(h, cudaStreamSynchronize(st));
   h->have_problem = true;
   return LCBA_OK;
@@ -943,10 +944,10 @@ static int pass_schur(lcba_t* h, const double* lam_host_or_null) {
             h->d_i8planes));
       if (h->i8_tma)
         KL(h, "schur", k_i8_syrk<true><<<(unsigned)ip.work.size(), I8_THREADS, ip.smem_bytes, h->stream>>>(
-              h->i8maps, h->d_i8planes, ip.NRG, h->d_i8work, h->d_i8partial, h->d_fail));
+              h->i8maps, h->d_i8planes, ip.NRG, h->d_i8work, h->d_i8partial, h->d_fail, h->d_stats));
       else
         KL(h, "schur", k_i8_syrk<false><<<(unsigned)ip.work.size(), I8_THREADS, ip.smem_bytes, h->stream>>>(
-              h->i8maps, h->d_i8planes, ip.NRG, h->d_i8work, h->d_i8partial, h->d_fail));
+              h->i8maps, h->d_i8planes, ip.NRG, h->d_i8work, h->d_i8partial, h->d_fail, h->d_stats));
       KL(h, "schur_reduce", k_i8_gather<<<dim3((unsigned)ip.tiles.size(), 16), 256, 0, h->stream>>>(
             h->d_i8partial, h->d_i8tiles, C, h->d_i8erow, pl.npairs, h->d_Sred));
       KL(h, "schur_reduce", k_add_cam_blocks<<<nblk(C * 121, 128), 128, 0, h->stream>>>(h->d_U, C, h->d_Sred));
@@ -1502,8 +1503,8 @@ extern "C" int lcba_comm_init(lcba_t* h, int32_t rank, int32_t nranks, const voi
 // debug: per-CTA cycle counters of the last k_schur launch (LCBA_SCHUR_STATS=1)
 extern "C" int lcba_debug_schur_stats(lcba_t* h, long long* out, int max_ctas, int* nkinds, int* nslices) {
   if (!h || !h->d_stats || !out) return LCBA_E_STATE;
-  const int nk = h->use_mma ? h->mplan.nkinds : h->plan.nkinds;
-  const int ns = h->use_mma ? h->mplan.nslices : h->plan.nslices;
+  const int nk = h->use_i8 ? 1 : (h->use_mma ? h->mplan.nkinds : h->plan.nkinds);
+  const int ns = h->use_i8 ? (int)h->i8plan.work.size() : (h->use_mma ? h->mplan.nslices : h->plan.nslices);
   const int n = std::min(max_ctas, ns * nk);
   cudaMemcpy(out, h->d_stats, (size_t)n * 4 * sizeof(long long), cudaMemcpyDeviceToHost);
   *nkinds = nk;

@@ -100,21 +100,33 @@ inline I8Plan make_i8_plan(int C, long long P, int sm_count) {
       pl.tiles.push_back(t);
     }
   }
-  const int nmain = (int)pl.tiles.size();
-  long long nranges = std::max<long long>(1, sm_count / nmain), ncorner = 0;
   if (fold) {
-    // the corner tile (left-over rows x left-over rows) has almost no tensor work but pays the fixed
-    // issue cost of every K block (~0.66 of a main tile's): it needs ~0.66 x as many CTAs as a main
-    // tile has K ranges, or it becomes the critical path (first attempt: 4 CTAs -> 7.8 ms)
-    I8Tile t{c0, last_m, c0, last_m, 0, 0, 0, 0};
+    I8Tile t{c0, last_m, c0, last_m, 0, 0, 0, 0};         // the corner: left-over rows x left-over rows
     pl.tiles.push_back(t);
-    nranges = std::max<long long>(1, (long long)(sm_count / (nmain + 0.66)));
-    ncorner = std::max<long long>(1, sm_count - nmain * nranges);
   }
-  nranges = std::min<long long>(nranges, pl.nkb);
+  // K ranges per tile: one CTA per SM in total, dealt so that the slowest tile finishes as early as possible.
+  // Cost of one K block of a tile, in cycles of the MMA warp (measured per tile kind with LCBA_SCHUR_STATS=1,
+  // tools/i8_stats.py, ring24 x 1 M): a fixed part (stage hand-over, waiting for operands) + one part per column
+  // block that grows with its width -- narrow instructions are far from free: a 16-column block costs half a
+  // 48-column one.  (The first version gave every main tile the same number of ranges: the tile that carries a
+  // second column block was 13 % slower than the rest and set the kernel's time.)
+  auto block_cost = [](int nrg) { return nrg <= 0 ? 0.0 : (nrg <= 2 ? 592.0 : (nrg <= 4 ? 812.0 : (nrg <= 6 ? 1181.0 : 1550.0))); };
+  std::vector<double> cost(pl.tiles.size());
+  std::vector<long long> nr(pl.tiles.size(), 1);
+  for (size_t ti = 0; ti < pl.tiles.size(); ++ti) cost[ti] = 507.0 + block_cost(pl.tiles[ti].n_nrg) + block_cost(pl.tiles[ti].n2_nrg);
+  for (long long left = (long long)sm_count - (long long)pl.tiles.size(); left > 0; --left) {
+    size_t worst = 0;
+    double tw = -1.0;
+    for (size_t ti = 0; ti < pl.tiles.size(); ++ti) {
+      const double tt = nr[ti] < pl.nkb ? cost[ti] / (double)nr[ti] : -1.0;
+      if (tt > tw) { tw = tt; worst = ti; }
+    }
+    if (tw < 0.0) break;                                    // every tile already has one CTA per K block
+    ++nr[worst];
+  }
   for (size_t ti = 0; ti < pl.tiles.size(); ++ti) {
     I8Tile& t = pl.tiles[ti];
-    const long long n = (int)ti < nmain ? nranges : std::min<long long>(ncorner, pl.nkb);
+    const long long n = std::min<long long>(nr[ti], pl.nkb);
     t.w0 = (int)pl.work.size();
     t.nw = (int)n;
     auto map_of = [&](int h) {
@@ -195,10 +207,19 @@ __device__ __forceinline__ void i8_bulk_g2s(uint32_t dst, const void* src, uint3
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// COLL: what happens to the A operand in the tensor core's collector: 0 nothing kept (the default), 1 ::fill (read
+// from shared memory and kept), 2 ::use (taken from the collector, kept), 3 ::lastuse (taken from the collector)
+template <int COLL>
 __device__ __forceinline__ void i8_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-               "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
-               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(0u) : "memory");
+#define I8_MMA_ASM(Q)                                                                                      \
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"                                          \
+               "tcgen05.mma.cta_group::1.kind::i8" Q " [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"         \
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(0u) : "memory")
+  if (COLL == 1) I8_MMA_ASM(".collector::a::fill");
+  else if (COLL == 2) I8_MMA_ASM(".collector::a::use");
+  else if (COLL == 3) I8_MMA_ASM(".collector::a::lastuse");
+  else I8_MMA_ASM("");
+#undef I8_MMA_ASM
 }
 __device__ __forceinline__ void i8_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -502,25 +523,44 @@ k_i8_make(const double* __restrict__ tab, const double* __restrict__ pts, const 
 }
 
 // ------------------------------------------------------------------------------ MMA issue plan
-struct I8Op { int i, j, nj, fresh; };
+struct I8Op { int i, j, nj, fresh, coll; };
+// The digit products of one k-step as tcgen05.mma instructions.  For a fixed slice i of A the slices j = 0..jmax of B
+// are adjacent in shared memory and their anti-diagonals i + j adjacent in TMEM, so up to 256 / NCOL of them go into
+// ONE instruction (N = nj NCOL).  Order: narrow instructions first, the widest last -- what sits in the tensor
+// pipe's queue while the issuing thread crosses a stage boundary (commit, mbarrier wait, fence) must be long enough
+// to cover it.  FIRST (the k-step after a flush): one instruction per product, the first to touch an
+// anti-diagonal overwrites it.
 template <int NCOL, bool FIRST>
 struct I8KstepPlan {
-  I8Op ops[16];
+  I8Op ops[32];
   int n;
   constexpr I8KstepPlan() : ops{}, n(0) {
-    for (int i = 0; i < I8_NS && i <= I8_DMAX; ++i) {
+    bool touched[I8_ND] = {};
+    for (int i = I8_NS - 1; i >= 0; --i) {
+      if (i > I8_DMAX) continue;
       const int jmax = (I8_NS - 1 < I8_DMAX - i) ? I8_NS - 1 : I8_DMAX - i;
-      int j = 0;
-      while (j <= jmax) {
-        // block d = i + j is initialised (accumulate = 0) by slice 0, except d = NS-1+i, which slice i
-        // is the first to touch (j = NS-1)
-        const bool fresh = FIRST && (i == 0 || j == I8_NS - 1);
-        int j1 = j;
-        while (j1 + 1 <= jmax && (j1 + 2 - j) * NCOL <= 256 && (FIRST && (i == 0 || j1 + 1 == I8_NS - 1)) == fresh) ++j1;
-        ops[n].i = i; ops[n].j = j; ops[n].nj = j1 - j + 1; ops[n].fresh = fresh ? 1 : 0;
-        ++n;
-        j = j1 + 1;
+      if (FIRST) {
+        for (int j = 0; j <= jmax; ++j) {
+          ops[n].i = i; ops[n].j = j; ops[n].nj = 1; ops[n].fresh = touched[i + j] ? 0 : 1; ops[n].coll = 0;
+          touched[i + j] = true;
+          ++n;
+        }
+      } else {
+        const int per = 256 / NCOL, cnt = jmax + 1;
+        int j = 0, rem = cnt % per;                     // the left-over (narrow) instruction goes first
+        while (j <= jmax) {
+          const int nj = (rem > 0) ? rem : per;
+          rem = 0;
+          ops[n].i = i; ops[n].j = j; ops[n].nj = nj; ops[n].fresh = 0; ops[n].coll = 0;
+          ++n;
+          j += nj;
+        }
       }
+    }
+    // consecutive MMAs on the same slice i of A: the first keeps A in the collector, the others take it from there
+    for (int q = 0; q < n; ++q) {
+      const bool prev = q > 0 && ops[q - 1].i == ops[q].i, next = q + 1 < n && ops[q + 1].i == ops[q].i;
+      ops[q].coll = prev ? (next ? 2 : 3) : (next ? 1 : 0);
     }
   }
 };
@@ -536,8 +576,12 @@ __device__ __forceinline__ void i8_issue_kstep(uint32_t tmem, uint32_t sA, uint3
   for (int q = 0; q < plan.n; ++q) {
     const uint64_t adesc = ((uint64_t)DESC_HI << 32) | (DESC_LO | (((sA + plan.ops[q].i * a_bytes) >> 4) & 0x3FFF));
     const uint64_t bdesc = ((uint64_t)DESC_HI << 32) | (DESC_LO | (((sB + plan.ops[q].j * b_bytes) >> 4) & 0x3FFF));
-    i8_mma(tmem + (uint32_t)((plan.ops[q].i + plan.ops[q].j) * NCOL), adesc, bdesc,
-           IDESC | ((uint32_t)(plan.ops[q].nj * NCOL >> 3) << 17), plan.ops[q].fresh ? 0u : 1u);
+    const uint32_t dcol = tmem + (uint32_t)((plan.ops[q].i + plan.ops[q].j) * NCOL);
+    const uint32_t idesc = IDESC | ((uint32_t)(plan.ops[q].nj * NCOL >> 3) << 17), accum = plan.ops[q].fresh ? 0u : 1u;
+    if (plan.ops[q].coll == 1) i8_mma<1>(dcol, adesc, bdesc, idesc, accum);
+    else if (plan.ops[q].coll == 2) i8_mma<2>(dcol, adesc, bdesc, idesc, accum);
+    else if (plan.ops[q].coll == 3) i8_mma<3>(dcol, adesc, bdesc, idesc, accum);
+    else i8_mma<0>(dcol, adesc, bdesc, idesc, accum);
   }
 }
 // one K block = two k-steps; column block 1 (NCOL1 columns per anti-diagonal, TMEM columns [0, 7 NCOL1)) and
@@ -562,7 +606,8 @@ __device__ __forceinline__ void i8_issue_block(bool first, uint32_t tmem, uint32
 template <bool TMA>
 __global__ void __launch_bounds__(I8_THREADS, 1)
 k_i8_syrk(const __grid_constant__ I8Maps maps, const unsigned char* __restrict__ planes, int NRG,
-          const I8Work* __restrict__ work, double* __restrict__ partial, int* __restrict__ fail) {
+          const I8Work* __restrict__ work, double* __restrict__ partial, int* __restrict__ fail,
+          long long* __restrict__ stats /* null, or per CTA: MMA warp (waiting at FULL, total), producer (waiting at EMPTY, total) cycles */) {
   extern __shared__ __align__(1024) uint8_t i8_smem[];
   __shared__ __align__(8) uint64_t s_bar[2 * I8_STAGES + 2];
   __shared__ uint32_t s_tmem;
@@ -599,7 +644,7 @@ k_i8_syrk(const __grid_constant__ I8Maps maps, const unsigned char* __restrict__
       if (lane == 0) {
         for (int it = 0; it < nkb; ++it) {
           const int st = it % I8_STAGES;
-          if (it >= I8_STAGES) i8_mbar_wait<true>(bar_empty + 8 * st, ((it / I8_STAGES) - 1) & 1, fail);
+          if (it >= I8_STAGES) i8_mbar_wait<false>(bar_empty + 8 * st, ((it / I8_STAGES) - 1) & 1, fail);
           i8_mbar_expect_tx(bar_full + 8 * st, (uint32_t)I8_NS * (a_bytes + b_bytes + b2_bytes));
           const uint32_t dstA = smem0 + st * STAGE_BYTES, dstB = dstA + A_REGION;
           const int kb = W.kb0 + it;
@@ -614,7 +659,7 @@ k_i8_syrk(const __grid_constant__ I8Maps maps, const unsigned char* __restrict__
     const bool mine = lane < 3 * I8_NS && (cb < 2 || W.n2_nrg > 0);
     for (int it = 0; it < nkb; ++it) {
       const int st = it % I8_STAGES;
-      if (it >= I8_STAGES) i8_mbar_wait<true>(bar_empty + 8 * st, ((it / I8_STAGES) - 1) & 1, fail);
+      if (it >= I8_STAGES) i8_mbar_wait<false>(bar_empty + 8 * st, ((it / I8_STAGES) - 1) & 1, fail);
       if (lane == 0) i8_mbar_expect_tx(bar_full + 8 * st, (uint32_t)I8_NS * (a_bytes + b_bytes + b2_bytes));
       __syncwarp();
       if (mine) {
@@ -630,13 +675,21 @@ k_i8_syrk(const __grid_constant__ I8Maps maps, const unsigned char* __restrict__
     // ---- MMA issuer: the highest warp id of its scheduler; one elected lane
     if (i8_elect_one()) {
       int since_flush = 0, nflush = 0;
+      long long t_wait = 0;
+      const long long t_begin = stats ? clock64() : 0;
       for (int it = 0; it < nkb; ++it) {
         const int st = it % I8_STAGES;
         if (since_flush == 0 && nflush > 0) {                // the accumulators are with the epilogue
           i8_mbar_wait<false>(bar_tempty, (nflush - 1) & 1, fail);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
-        i8_mbar_wait<false>(bar_full + 8 * st, (it / I8_STAGES) & 1, fail);
+        if (stats) {
+          const long long w0 = clock64();
+          i8_mbar_wait<false>(bar_full + 8 * st, (it / I8_STAGES) & 1, fail);
+          t_wait += clock64() - w0;
+        } else {
+          i8_mbar_wait<false>(bar_full + 8 * st, (it / I8_STAGES) & 1, fail);
+        }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sA = smem0 + st * STAGE_BYTES, sB = sA + A_REGION;
         const bool first = since_flush == 0;
@@ -662,6 +715,7 @@ k_i8_syrk(const __grid_constant__ I8Maps maps, const unsigned char* __restrict__
           ++nflush;
         }
       }
+      if (stats) { stats[4 * blockIdx.x] = t_wait; stats[4 * blockIdx.x + 1] = clock64() - t_begin; }
     }
   } else {
     // ---- epilogue: TMEM -> FP64 registers (thread = TMEM lane = tile row)
