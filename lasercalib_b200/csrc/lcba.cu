@@ -1189,7 +1189,12 @@ extern "C" int lcba_solve(lcba_t* h, const lcba_options* opt_in, lcba_result* re
     static const bool env_off = getenv("LCBA_GRAPH") && atoi(getenv("LCBA_GRAPH")) == 0;
     if (env_off) h->use_graphs = false;
   }
-  const bool graphs = h->solves_on_problem >= 1;      // second solve on this resident problem onwards
+  // Replay from the second solve on a resident problem onwards, where launches matter: single GPU (with NCCL
+  // all-reduces captured inside, a replay is SLOWER than direct launches: 4.48 vs 4.28 ms per iteration at 2 GPUs,
+  // 2.12 vs 1.80 at 8) and fewer than 8 M observations (above, an iteration is several ms of long kernels: A/B on
+  // one box, ring24 x 1 M: 8.06 / 8.36 vs 8.12 / 8.13 ms, and the capture + instantiation of the four graphs
+  // would fall into the second solve)
+  const bool graphs = h->solves_on_problem >= 1 && !h->comm && h->N < (8LL << 20);
   h->solves_on_problem++;
   const int gkey = h->fix_cameras * 2 + h->shared_intr;
   const long long n_cam = h->fix_cameras ? 0 : (h->shared_intr ? 3 + 8LL * h->C : (long long)h->C * NCP);
