@@ -111,6 +111,12 @@ def schur_flops(k_hist_counts, n_obs):
     return float(np.sum(per_point * k_hist_counts) + 300.0 * n_obs)
 
 
+def _sha16(path):
+    import hashlib
+    with open(path, "rb") as f:
+        return hashlib.sha256(f.read()).hexdigest()[:16]
+
+
 def i8_ops(C, P):
     """int8 tensor work of one k_i8_syrk launch (schur_i8.cuh): (algorithmic, executed) in ops (1 MAC = 2).
     Algorithmic: the 26 digit products (i + j <= 6) of the lower triangle of the (11C+1)-row SYRK over
@@ -340,8 +346,13 @@ def main():
         try:   # dram bytes per launch from the committed `ncu --set full` capture of THIS kernel set and workload
             with open(os.path.join(REPO, "profiles", "r02_traffic.json")) as f:
                 tr = json.load(f)
+            # the capture is only valid for the kernel sources it was taken with: kernels_sha16 maps each kernel
+            # to the hash of its source file at capture time (tools/ncu_summary.py stamp)
+            def fresh(kernel):
+                rec = tr.get("kernels_sha16", {}).get(kernel)
+                return rec is not None and rec[1] == _sha16(os.path.join(REPO, "lasercalib_b200", "csrc", rec[0]))
             if ws == 1 and tr.get("n_obs") == N:
-                t = tr["dram_bytes_per_launch"]
+                t = {k: v for k, v in tr["dram_bytes_per_launch"].items() if fresh(k)}
                 if roof is not None and "i8_rowmax" in prof:
                     roof["traffic"] = t.get("k_i8_syrk")
                     roof["traffic_helpers"] = (t.get("k_i8_make", 0) + t.get("k_i8_rowmax", 0)) or None

@@ -252,6 +252,12 @@ int lcba_debug_i8_plan(int32_t C, int64_t P, int32_t sm_count, int32_t* tiles_ou
                        int32_t* work_out, int32_t max_work, int32_t* nwork_out, int32_t* nrg_out,
                        int64_t* nkb_out);
 
+/* Host-only helper of the sharding layer (lasercalib_b200/dist.py): 1 when v[0..n) is non-decreasing.  The
+ * reference keeps its observations point-major (scripts/get_points3d.py:74-86); the host mirror must verify
+ * that before it may cut contiguous observation ranges, on every call (the arrays are the caller's).  One
+ * streaming read on up to `threads` threads (numpy needs two reads and a temporary: 60 ms for 24 M indices). */
+int lcba_host_is_nondecreasing_i64(const int64_t* v, int64_t n, int32_t threads);
+
 #ifdef __cplusplus
 }
 #endif

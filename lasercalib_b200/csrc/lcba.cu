@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <nvtx3/nvToolsExt.h>
@@ -1644,4 +1645,24 @@ extern "C" int lcba_debug_tr2d(double B00, double B01, double B11, double g0, do
   p_out[1] = t.p1;
   if (newton_out) *newton_out = t.newton;
   return LCBA_OK;
+}
+
+// host-only: is v[0..n) non-decreasing?  (dist.py: may the observation arrays be cut into contiguous ranges?)
+extern "C" int lcba_host_is_nondecreasing_i64(const int64_t* v, int64_t n, int32_t threads) {
+  if (!v || n < 2) return 1;
+  const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(threads, 16), n / (1 << 20)));
+  std::vector<int> ok(nt, 1);
+  auto piece = [&](int i) {
+    const int64_t a = n * i / nt, b = std::min<int64_t>(n, n * (i + 1) / nt + 1);      // one element of overlap
+    int64_t bad = 0;
+    for (int64_t k = a + 1; k < b; ++k) bad |= (int64_t)(v[k] < v[k - 1]);
+    ok[i] = bad ? 0 : 1;
+  };
+  if (nt == 1) { piece(0); return ok[0]; }
+  std::vector<std::thread> th;
+  for (int i = 1; i < nt; ++i) th.emplace_back(piece, i);
+  piece(0);
+  for (auto& t : th) t.join();
+  for (int i = 0; i < nt; ++i) if (!ok[i]) return 0;
+  return 1;
 }

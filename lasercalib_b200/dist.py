@@ -58,10 +58,46 @@ def shard_bounds(point_ind, n_points, nranks):
     return b
 
 
-def _is_point_major(point_ind):
+def _nondecreasing(a, lo, hi):
+    """a[lo:hi] is non-decreasing.  Contiguous int64 (the reference's index dtype) goes through the host
+    helper of liblcba.so: one streaming read on a few threads (24 M indices: numpy's two reads + temporary
+    take ~60 ms on one thread); anything else through numpy."""
+    n = hi - lo
+    if n < 2:
+        return True
+    if a.dtype == np.int64 and a.flags.c_contiguous and a.ndim == 1:
+        try:
+            from . import _cabi
+            lib = _cabi.load()
+            nthr = max(1, min(4, (os.cpu_count() or 1) // max(1, world()[1])))
+            return bool(lib.lcba_host_is_nondecreasing_i64(a.ctypes.data + 8 * lo, n, nthr))
+        except (ImportError, OSError, AttributeError):
+            pass
+    return bool(np.all(a[lo + 1:hi] >= a[lo:hi - 1]))
+
+
+def _is_point_major(point_ind, collective=False):
     """O(N) monotonicity check, every time: a cached answer keyed on the buffer address could be
-    stale for a different or mutated array that reuses the address."""
-    return bool(point_ind.size < 2 or np.all(point_ind[1:] >= point_ind[:-1]))
+    stale for a different or mutated array that reuses the address.
+    collective=True (every rank of the torch.distributed job calls this with the SAME array): each rank
+    checks one N / world_size piece (with one element of overlap) and the verdicts are combined with a
+    one-element MIN all-reduce -- at 8 ranks the full check of 24 M int64 indices in every process was
+    most of the 32 ms a sharded bundleAdjust call spent before its first kernel."""
+    n = point_ind.size
+    if n < 2:
+        return True
+    rank, ws, _ = world()
+    if collective and ws > 1:
+        import torch
+        import torch.distributed as dist
+        lo, hi = (n * rank) // ws, min(n, (n * (rank + 1)) // ws + 1)
+        ok = _nondecreasing(point_ind, lo, hi)
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" \
+            else torch.device("cpu")
+        t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(int(t.item()))
+    return _nondecreasing(point_ind, 0, n)
 
 
 def _check_shards(bounds, counts_fn, nranks):
@@ -77,16 +113,19 @@ def _check_shards(bounds, counts_fn, nranks):
                              "observations): use fewer ranks" % (nranks, r, npts, nobs))
 
 
-def shard_problem(points3D, points2D, camera_ind, point_ind, weights, rank, nranks, bounds=None):
+def shard_problem(points3D, points2D, camera_ind, point_ind, weights, rank, nranks, bounds=None,
+                  collective=False):
     """This rank's slice: points [lo, hi), the observations that reference them (local point
     indices), all cameras implied.  Returns dict(pts, points_2d, camera_ind, point_ind,
     weights, lo, hi, obs_sel, pt_offset); obs_sel indexes the caller's observation arrays (a
     slice for point-major input, an index array otherwise); local point index =
-    point_ind - pt_offset (point-major input keeps views of the caller's arrays: no copies)."""
+    point_ind - pt_offset (point-major input keeps views of the caller's arrays: no copies).
+    collective=True: all ranks of the job are inside this call with the same arrays (rank and
+    nranks are the job's): the O(N) order check is split over the ranks."""
     point_ind = np.asarray(point_ind)
     P = points3D.shape[0]
     N = point_ind.size
-    if N > 1 and bounds is None and _is_point_major(point_ind):
+    if N > 1 and bounds is None and _is_point_major(point_ind, collective and nranks == world()[1] and rank == world()[0]):
         # point-major input (the reference's order): shards are contiguous observation ranges,
         # found by binary search; the observation arrays are sliced, not copied
         b = np.zeros(nranks + 1, dtype=np.int64)
@@ -140,6 +179,19 @@ def connect_engine(engine):
     _process_comm[ws] = True
 
 
+_pinned_stage = [None]
+
+
+def _pinned_f64(n):
+    """A cached pinned float64 host buffer of at least n elements (grown geometrically)."""
+    import torch
+    t = _pinned_stage[0]
+    if t is None or t.numel() < n:
+        t = torch.empty(max(n, 2 * (t.numel() if t is not None else 0)), dtype=torch.float64, pin_memory=True)
+        _pinned_stage[0] = t
+    return t[:n]
+
+
 def allgather_rows(local, bounds, out=None):
     """Concatenate per-rank row blocks (rank r holds rows bounds[r]:bounds[r+1]) on every rank.
     `out` (total rows x width, float64) is filled in place when given.  One collective into a
@@ -167,7 +219,14 @@ def allgather_rows(local, bounds, out=None):
         outs = [torch.empty_like(buf) for _ in range(ws)]
         dist.all_gather(outs, buf)
         big = torch.cat(outs, dim=0)
-    host = big.cpu().numpy().reshape(ws, mx, width)
+    if dev.type == "cuda":
+        # one D2H copy into a cached PINNED staging buffer (a pageable `.cpu()` of 24 MB cost most of the
+        # 13.6 ms this call took at 8 ranks), then the rank blocks go to their rows of `out`
+        stage = _pinned_f64(ws * mx * width).view(ws * mx, width)
+        stage.copy_(big)
+        host = stage.numpy().reshape(ws, mx, width)
+    else:
+        host = big.numpy().reshape(ws, mx, width)
     if out is None:
         out = np.empty((int(bounds[ws] - bounds[0]), width))
     for r in range(ws):

@@ -271,7 +271,7 @@ class PySBA:
                 eng.set_params(cams0, shard["pts0_of"](pts0))
             else:
                 shard = _dist.shard_problem(pts0, self.points2D, self.cameraIndices,
-                                            self.point2DIndices, w, rank, ws)
+                                            self.point2DIndices, w, rank, ws, collective=True)
                 lo, hi = shard["lo"], shard["hi"]
                 shard["pts0_of"] = lambda p, lo=lo, hi=hi: np.ascontiguousarray(p[lo:hi])
                 eng.set_problem(cams0, shard["pts"], shard["points_2d"], shard["camera_ind"],

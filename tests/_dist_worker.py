@@ -32,7 +32,17 @@ def main():
     sc = np.hstack((np.sqrt(np.einsum("caa->ca", U)).ravel(), np.sqrt(np.einsum("paa->pa", V)).ravel()))
     S_ref, rhs_ref, _ = O.reduced_camera_system(U, gc, V, gp, W, ci, pi, lam, sc)
     # ---- this rank's shard ----
-    sh = D.shard_problem(pb["pts0"], pb["points_2d"], ci, pi, None, rank, ws)
+    sh = D.shard_problem(pb["pts0"], pb["points_2d"], ci, pi, None, rank, ws, collective=True)
+    ref_sh = D.shard_problem(pb["pts0"], pb["points_2d"], ci, pi, None, rank, ws)          # full local check
+    assert sh["lo"] == ref_sh["lo"] and sh["hi"] == ref_sh["hi"] and np.array_equal(sh["bounds"], ref_sh["bounds"])
+    # the order check split over the ranks: one verdict on every rank, wherever the violation sits
+    srt = np.sort(pi)
+    assert D._is_point_major(srt, collective=True) and D._is_point_major(srt)
+    n = srt.size
+    for pos in (1, n // ws, n // ws - 1, (n * (ws - 1)) // ws, n - 1):     # piece interiors and piece borders
+        bad = srt.copy()
+        bad[pos - 1] = bad[pos] + 1
+        assert not D._is_point_major(bad) and not D._is_point_major(bad, collective=True), pos
     b = sh["bounds"]
     sh["point_ind"] = sh["point_ind"] - sh["pt_offset"]        # local indices for the oracle
     assert b[0] == 0 and b[-1] == P and np.all(np.diff(b) >= 0)

@@ -1,6 +1,8 @@
 """Summaries of ncu captures for profiles/ (run where the .ncu-rep / csv files are):
   python tools/ncu_summary.py launches <gpu__time_duration csv> <out csv>
   python tools/ncu_summary.py full <`ncu -i x.ncu-rep --page raw --csv` output> <out txt> <out traffic json> <n_obs>
+  python tools/ncu_summary.py stamp <traffic json>      record, per kernel, the hash of the source file it lives in
+                                                         (bench.py ignores entries whose source changed since)
 """
 import csv
 import json
@@ -40,6 +42,24 @@ def read_csv(path):
 def rows_of(path):          # --page raw: header, units row, one row per launch
     h, rows = read_csv(path)
     return h, rows[0], rows[1:]
+
+
+KERNEL_FILES = {"k_i8_syrk": "schur_i8.cuh", "k_i8_make": "schur_i8.cuh", "k_i8_rowmax": "schur_i8.cuh",
+                "k_jacobian_blocks": "eval.cuh"}
+
+
+def stamp(path):
+    import hashlib
+    import os
+    with open(path) as f:
+        tr = json.load(f)
+    csrc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lasercalib_b200", "csrc")
+    tr["kernels_sha16"] = {}
+    for k, fn in KERNEL_FILES.items():
+        with open(os.path.join(csrc, fn), "rb") as f:
+            tr["kernels_sha16"][k] = [fn, hashlib.sha256(f.read()).hexdigest()[:16]]
+    with open(path, "w") as f:
+        json.dump(tr, f, indent=1)
 
 
 def launches(src, dst):     # --metrics gpu__time_duration.sum --csv: one row per (launch, metric)
@@ -99,5 +119,7 @@ def full(src, dst_txt, dst_json, n_obs):
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3])
+    elif sys.argv[1] == "stamp":
+        stamp(sys.argv[2])
     else:
         full(sys.argv[2], sys.argv[3], sys.argv[4], sys.argv[5])
