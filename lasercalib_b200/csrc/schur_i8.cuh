@@ -424,7 +424,11 @@ k_i8_make(const double* __restrict__ tab, const double* __restrict__ pts, const 
   for (int i = t; i < I8_GROUP_ROWS * I8_VAL_LD; i += blockDim.x) s_val[i] = 0ull;       // padding rows / column 63 stay 0
   __syncthreads();
   const bool worker = t < I8_PTS * gc;
-  const int q = worker ? t / gc : 0, cl = worker ? t % gc : 0, cam = c0 + cl;
+  // point lane of a thread: slots 2j, 2j + 1 (the two point lanes of a half-warp when gc = 8) take lanes j and j + 8:
+  // their staging columns then differ by 24 words = 8 banks and the 64-bit stores of phase 1 are conflict-free
+  // (with neighbouring lanes, 3 words apart, one bank of the 16 was hit twice by every store: 2 wavefronts each)
+  const int slot = worker ? t / gc : 0;
+  const int q = slot < 16 ? (slot >> 1) + 8 * (slot & 1) : slot, cl = worker ? t % gc : 0, cam = c0 + cl;
   const bool zthread = (g == (int)gridDim.y - 1) && t >= 168 && t < 168 + I8_PTS;
   const int zrow = NCP * C - rg0 * 8;                        // local row of z in the last group
   const long long nkb = (P + I8_PTS - 1) / I8_PTS;
