@@ -188,3 +188,30 @@ def test_int8_schur_plan_covers_the_lower_triangle_once():
                 assert min(two) >= max(one), (cams, nws)     # the two-block tiles get at least as many CTAs
             alg, exe = bench.i8_ops(cams, P)
             assert exe == 26 * 2.0 * 128 * cols * nkb.value * 64 and alg <= exe
+
+
+def test_host_order_check_of_the_index_array():
+    """lcba_host_is_nondecreasing_i64 (host-only, no GPU): the sharding layer's check that the caller's
+    point indices are point-major (scripts/get_points3d.py:74-86 order) -- every thread count, violations
+    inside a thread's piece and exactly on the piece borders, tiny and empty inputs; and dist._nondecreasing
+    (which routes contiguous int64 through it and everything else through numpy) agrees on sub-ranges."""
+    from lasercalib_b200 import _cabi, dist as D
+    lib = _cabi.load()
+    rng = np.random.default_rng(0)
+    n = 5_000_000
+    a = np.sort(rng.integers(0, 200_000, n))
+    ptr = lambda v: v.ctypes.data
+    for thr in (1, 2, 3, 4, 8, 64):
+        assert lib.lcba_host_is_nondecreasing_i64(ptr(a), n, thr) == 1
+        for pos in (1, n - 1, n // 2, n // 3, n // 4, n // 4 + 1, n // 4 - 1, 3 * n // 4, 2 * (n // 3)):
+            b = a.copy()
+            b[pos - 1] = b[pos] + 1
+            assert lib.lcba_host_is_nondecreasing_i64(ptr(b), n, thr) == 0, (thr, pos)
+            assert lib.lcba_host_is_nondecreasing_i64(ptr(b) + 8 * pos, n - pos, thr) == 1
+    assert lib.lcba_host_is_nondecreasing_i64(ptr(a), 0, 4) == 1 and lib.lcba_host_is_nondecreasing_i64(ptr(a), 1, 4) == 1
+    assert lib.lcba_host_is_nondecreasing_i64(None, 10, 4) == 1
+    b = a.copy()
+    b[1000] = -1
+    assert not D._nondecreasing(b, 0, n) and D._nondecreasing(b, 1000, n) and not D._nondecreasing(b, 999, 1002)
+    assert D._nondecreasing(a[::2], 0, n // 2) and D._nondecreasing(a.astype(np.int32), 0, n)      # numpy route
+    assert not D._nondecreasing(b[::2], 0, n // 2) and not D._nondecreasing(b.astype(np.int32), 0, n)
