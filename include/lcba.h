@@ -252,6 +252,11 @@ int lcba_debug_i8_plan(int32_t C, int64_t P, int32_t sm_count, int32_t* tiles_ou
                        int32_t* work_out, int32_t max_work, int32_t* nwork_out, int32_t* nrg_out,
                        int64_t* nkb_out);
 
+/* Measurement switch (tools/peer_ab.py): all-reduce through NVLink peer memory (csrc/peer_reduce.cuh; needs LCBA_PEER_REDUCE=1 or 2 at
+ * lcba_comm_init so that every rank has mapped every peer's block) or through ncclAllReduce, from the next call on.  Collective in the
+ * sense that every rank must switch at the same point.  Returns 1 if the peer path is active afterwards. */
+int lcba_debug_peer_reduce(lcba_t* h, int enable);
+
 /* Host-only helper of the sharding layer (lasercalib_b200/dist.py): 1 when v[0..n) is non-decreasing.  The
  * reference keeps its observations point-major (scripts/get_points3d.py:74-86); the host mirror must verify
  * that before it may cut contiguous observation ranges, on every call (the arrays are the caller's).  One

@@ -21,7 +21,7 @@ SYMBOLS = ["lcba_version", "lcba_create", "lcba_destroy", "lcba_last_error", "lc
            "lcba_get_trace", "lcba_get_grad", "lcba_get_profile", "lcba_linearize",
            "lcba_time_device", "lcba_nccl_unique_id", "lcba_comm_init", "lcba_debug_tr2d",
            "lcba_sq_normal", "lcba_debug_schur_stats", "lcba_debug_mma_plan",
-           "lcba_set_iteration_callback", "lcba_debug_i8_plan", "lcba_host_is_nondecreasing_i64"]
+           "lcba_set_iteration_callback", "lcba_debug_i8_plan", "lcba_host_is_nondecreasing_i64", "lcba_debug_peer_reduce"]
 
 
 class Options(C.Structure):
@@ -108,6 +108,7 @@ def load():
     lib.lcba_debug_schur_stats.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.lcba_debug_i8_plan.argtypes = [i32, i64, i32, vp, i32, vp, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i64)]
     lib.lcba_host_is_nondecreasing_i64.argtypes = [vp, i64, i32]
+    lib.lcba_debug_peer_reduce.argtypes = [vp, i32]
     lib.lcba_debug_tr2d.argtypes = [dbl, dbl, dbl, dbl, dbl, dbl, pd, C.POINTER(C.c_int)]
     _lib = lib
     return lib

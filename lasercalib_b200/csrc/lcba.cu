@@ -23,6 +23,7 @@
 #include "schur.cuh"
 #include "schur_mma.cuh"
 #include "schur_i8.cuh"
+#include "peer_reduce.cuh"
 #include "variants.cuh"
 
 using namespace lcba;
@@ -35,6 +36,7 @@ struct NcclApi {
   int (*GetUniqueId)(ncclUniqueId*) = nullptr;
   int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;    // optional
   int (*CommDestroy)(ncclComm_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
 };
@@ -58,6 +60,7 @@ static bool nccl_load(std::string& err) {
   LOADSYM(CommDestroy, "ncclCommDestroy")
   LOADSYM(GetErrorString, "ncclGetErrorString")
 #undef LOADSYM
+  *(void**)(&g_nccl.AllGather) = dlsym(g_nccl.lib, "ncclAllGather");
   return true;
 }
 
@@ -162,6 +165,18 @@ static std::string g_last_error;
 // lcba_comm_init that carries a unique id, attached by later handles (id == NULL).
 static ncclComm_t g_comm = nullptr;
 static int g_comm_rank = -1, g_comm_nranks = 0, g_comm_device = -1;
+// Peer-memory all-reduce of the process (peer_reduce.cuh): set up next to the communicator; ok == false -> NCCL
+struct PeerState {
+  bool ok = false;
+  void* block = nullptr;                 // own block (cudaMalloc: exportable)
+  void* opened[PEER_MAX_RANKS] = {};     // peers' blocks as mapped here
+  PeerPtrs ptrs = {};
+  unsigned epoch = 0;
+  int* h_fail = nullptr;                 // mapped host word the kernel raises on a timed-out wait
+  int* d_fail = nullptr;
+};
+static PeerState g_peer;
+static bool g_peer_available = false;    // mapped on every rank (the route may still be switched off)
 static void set_error(lcba_t* h, const std::string& s) {
   if (h) h->err = s;
   g_last_error = s;
@@ -232,6 +247,14 @@ static int check_launch(lcba_t* h, const char* what) {
 
 static int allreduce(lcba_t* h, double* p, size_t n, int op) {
   if (!h->comm) return LCBA_OK;
+  if (g_peer.ok && n <= PEER_SLOT) {
+    // one kernel over NVLink peer memory (peer_reduce.cuh); same call order on every rank, like NCCL
+    ++g_peer.epoch;
+    k_peer_allreduce<<<peer_grid(n), PEER_THREADS, 0, h->stream>>>(g_peer.ptrs, h->rank, h->nranks, g_peer.epoch, p, n,
+                                                                   op == NCCL_MAX ? PEER_OP_MAX : PEER_OP_SUM, g_peer.d_fail);
+    h->launches++;
+    return LCBA_OK;
+  }
   int rc = g_nccl.AllReduce(p, p, n, NCCL_FLOAT64, op, h->comm, h->stream);
   if (rc != 0) {
     set_error(h, std::string("ncclAllReduce: ") + g_nccl.GetErrorString(rc));
@@ -1104,6 +1127,10 @@ static int pass_trial(lcba_t* h) {
 static int read_ctl(lcba_t* h) {
   LCBA_CUDA(h, cudaMemcpyAsync(h->h_ctl, h->d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, h->stream));
   LCBA_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (h->comm && g_peer.ok && *(volatile int*)g_peer.h_fail) {
+    set_error(h, "peer all-reduce: a rank did not arrive within the time limit");
+    return LCBA_E_NCCL;
+  }
   return check_launch(h, "solver");
 }
 
@@ -1474,6 +1501,80 @@ extern "C" int lcba_nccl_unique_id(void* id_out128) {
   return LCBA_OK;
 }
 
+// Map every rank's peer block (cudaIpc handles exchanged with ncclAllGather).  All ranks must agree on the
+// outcome: the verdicts are summed with NCCL, anything short of "all ranks mapped all peers" disables the path
+// everywhere.
+static void peer_setup(lcba_t* h) {
+  PeerState& ps = g_peer;
+  const int n = h->nranks, rank = h->rank;
+  for (int r = 0; r < PEER_MAX_RANKS; ++r)
+    if (ps.opened[r]) { cudaIpcCloseMemHandle(ps.opened[r]); ps.opened[r] = nullptr; }
+  if (ps.block) { cudaFree(ps.block); ps.block = nullptr; }
+  ps.ok = false;
+  ps.epoch = 0;
+  // Opt-in: measured against ncclAllReduce inside one job (tools/peer_ab.py, 8 GPUs, 24 cameras x 1 M points) the
+  // peer route is 0.7 % SLOWER per iteration (1.585 vs 1.574 ms): NCCL's small all-reduces are not what the fixed
+  // cost of an iteration consists of.  LCBA_PEER_REDUCE=1: map and use; 2: map, keep NCCL until
+  // lcba_debug_peer_reduce switches (A/B tool); unset / 0: NCCL only, nothing is mapped.
+  const char* env = getenv("LCBA_PEER_REDUCE");
+  const int mode = env ? atoi(env) : 0;
+  if (mode <= 0) return;
+  bool mine = n > 1 && n <= PEER_MAX_RANKS && g_nccl.AllGather != nullptr;
+  cudaIpcMemHandle_t hdl;
+  memset(&hdl, 0, sizeof(hdl));
+  if (mine && !ps.h_fail)
+    mine = cudaHostAlloc((void**)&ps.h_fail, sizeof(int), cudaHostAllocMapped) == cudaSuccess &&
+           cudaHostGetDevicePointer((void**)&ps.d_fail, ps.h_fail, 0) == cudaSuccess;
+  if (mine) {
+    *ps.h_fail = 0;
+    mine = cudaMalloc(&ps.block, peer_block_bytes()) == cudaSuccess &&
+           cudaMemset(ps.block, 0, peer_block_bytes()) == cudaSuccess &&
+           cudaIpcGetMemHandle(&hdl, ps.block) == cudaSuccess;
+  }
+  cudaGetLastError();
+  // exchange the handles (every rank takes part, whatever its own verdict so far)
+  std::vector<cudaIpcMemHandle_t> all(n);
+  unsigned char* d_h = nullptr;
+  bool xch = g_nccl.AllGather != nullptr && cudaMalloc((void**)&d_h, (size_t)n * sizeof(hdl)) == cudaSuccess;
+  if (xch) {
+    cudaMemcpyAsync(d_h + (size_t)rank * sizeof(hdl), &hdl, sizeof(hdl), cudaMemcpyHostToDevice, h->stream);
+    xch = g_nccl.AllGather(d_h + (size_t)rank * sizeof(hdl), d_h, sizeof(hdl), /*ncclInt8*/ 0, h->comm, h->stream) == 0 &&
+          cudaMemcpyAsync(all.data(), d_h, (size_t)n * sizeof(hdl), cudaMemcpyDeviceToHost, h->stream) == cudaSuccess &&
+          cudaStreamSynchronize(h->stream) == cudaSuccess;
+  }
+  if (d_h) cudaFree(d_h);
+  mine = mine && xch;
+  if (mine) {
+    for (int r = 0; r < n && mine; ++r) {
+      void* q = ps.block;
+      if (r != rank) {
+        mine = cudaIpcOpenMemHandle(&q, all[r], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+        if (mine) ps.opened[r] = q;
+      }
+      if (mine) {
+        ps.ptrs.sym[r] = (double*)q;
+        ps.ptrs.flags[r] = (unsigned*)((char*)q + 2 * PEER_SLOT * sizeof(double));
+      }
+    }
+  }
+  cudaGetLastError();
+  // agreement (also the barrier after which every block is zeroed and mapped): sum of the verdicts over NCCL
+  double* d_v = nullptr;
+  double v = mine ? 1.0 : 0.0, sum = 0.0;
+  if (cudaMalloc((void**)&d_v, 8) == cudaSuccess &&
+      cudaMemcpyAsync(d_v, &v, 8, cudaMemcpyHostToDevice, h->stream) == cudaSuccess &&
+      g_nccl.AllReduce(d_v, d_v, 1, NCCL_FLOAT64, NCCL_SUM, h->comm, h->stream) == 0 &&
+      cudaMemcpyAsync(&sum, d_v, 8, cudaMemcpyDeviceToHost, h->stream) == cudaSuccess &&
+      cudaStreamSynchronize(h->stream) == cudaSuccess)
+    ps.ok = mine && sum == (double)n;
+  if (d_v) cudaFree(d_v);
+  g_peer_available = ps.ok;
+  if (mode == 2) ps.ok = false;
+  cudaGetLastError();
+  if (getenv("LCBA_PEER_VERBOSE"))
+    fprintf(stderr, "[lcba] rank %d/%d: peer all-reduce %s\n", rank, n, ps.ok ? "on (NVLink peer memory)" : "off (NCCL)");
+}
+
 extern "C" int lcba_comm_init(lcba_t* h, int32_t rank, int32_t nranks, const void* id128) {
   if (!h || nranks < 1 || rank < 0 || rank >= nranks) { set_error(h, "lcba_comm_init: bad argument"); return LCBA_E_ARG; }
   std::string err;
@@ -1503,7 +1604,19 @@ extern "C" int lcba_comm_init(lcba_t* h, int32_t rank, int32_t nranks, const voi
   h->comm = comm;
   h->rank = rank;
   h->nranks = nranks;
+  peer_setup(h);        // optional: any failure leaves the NCCL path in place
   return LCBA_OK;
+}
+
+// measurement switch: route the all-reduces through NVLink peer memory (1) or NCCL (0) from now on; every rank
+// must call it at the same point of the program.  Returns 1 when the peer path is (now) active, 0 when it is off
+// or was never set up (LCBA_PEER_REDUCE=0, mapping failed on some rank).
+extern "C" int lcba_debug_peer_reduce(lcba_t* h, int enable) {
+  if (!h || !h->comm) return 0;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  g_peer.ok = g_peer_available && enable != 0;
+  return g_peer.ok ? 1 : 0;
 }
 
 // debug: per-CTA cycle counters of the last k_schur launch (LCBA_SCHUR_STATS=1)
