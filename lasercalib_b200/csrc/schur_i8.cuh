@@ -15,9 +15,11 @@
 //                   [K block of 64 kappa = 21 points + 1 zero][slice][row group of 8][k-step 2][k half 2][8][16]
 //   k_i8_syrk     : one CTA = one output tile (128 rows x <= 64 columns, the 7 anti-diagonals d = i + j
 //                   side by side in TMEM) x a range of K blocks; warps 0-3 epilogue (TMEM -> FP64 registers
-//                   before an int32 can overflow), warp 4 bulk-copy producer (one cp.async.bulk per lane,
-//                   12 per K block = 2 k-steps), warp 5 MMA issuer (elect.sync, compile-time MMA plan:
-//                   slice i of the rows against slices 0..6-i of the columns in ONE instruction, N <= 256)
+//                   before an int32 can overflow), warp 4 producer (three cp.async.bulk.tensor.4d loads per
+//                   K block = 2 k-steps: all six slices of A, B1, B2; fallback: one 1-D bulk copy per lane),
+//                   warp 5 MMA issuer (elect.sync, compile-time MMA plan: slice i of the rows against slices
+//                   0..6-i of the columns in ONE instruction, N <= 256, A kept in the collector, widest last);
+//                   K ranges per tile weighted by the measured cost of a K block (make_i8_plan)
 //   k_i8_gather   : per-CTA partials -> the pair-block layout of Sred (fixed order, no atomics)
 #pragma once
 #include <cuda.h>
