@@ -1773,8 +1773,13 @@ extern "C" int lcba_host_is_nondecreasing_i64(const int64_t* v, int64_t n, int32
   };
   if (nt == 1) { piece(0); return ok[0]; }
   std::vector<std::thread> th;
-  for (int i = 1; i < nt; ++i) th.emplace_back(piece, i);
+  int started = 1;                                  // pieces [started, nt) fall back to this thread
+  try {
+    for (int i = 1; i < nt; ++i) { th.emplace_back(piece, i); started = i + 1; }
+  } catch (...) {                                   // no more threads: nothing may cross the C boundary
+  }
   piece(0);
+  for (int i = started; i < nt; ++i) piece(i);
   for (auto& t : th) t.join();
   for (int i = 0; i < nt; ++i) if (!ok[i]) return 0;
   return 1;
